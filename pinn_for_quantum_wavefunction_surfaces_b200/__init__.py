@@ -1,0 +1,29 @@
+"""B200-native PINN residual-and-gradient hot path for the parametric H2+ model
+(arXiv:2211.04607) as implemented by slitvinov/PINN_for_quantum_wavefunction_surfaces.
+
+Only the hot path lives here: the fused loss + parameter-gradient kernels behind a C ABI
+(``libpinn_b200.so``, ``include/pinn_b200.h``) and the Python mirror of the reference's
+call sites:
+
+* ``PinnLossPoc`` / ``PinnLossTrainPy`` - ``torch.autograd.Function`` replacements of
+  ``NN_ion.LossFunctions`` (poc/main.py:341-355) and of the inline block train.py:41-57
+* ``fields``          - fused ``parametricPsi`` + ``hamiltonian`` (poc/main.py:321, 118)
+* ``patch_nn_ion``    - monkey-patches an ``NN_ion`` class so the reference training loop runs unchanged
+* ``run_train_py``    - runs the reference ``train.py`` with lines 41-57 routed through the kernel
+
+There is no CPU fallback: importing works anywhere, but every compute entry raises if the
+CUDA library or a B200 is missing.
+"""
+from .params import (N_THETA, POC_TENSOR_NAMES, TRAINPY_TENSOR_NAMES, pack_poc, unpack_poc, pack_trainpy,
+                     unpack_trainpy, FINE_TUNE_GRAD_MASK)
+from ._lib import lib, Handle, PinnError, library_path
+from .ops import (PinnLossPoc, PinnLossTrainPy, loss_poc, loss_trainpy, fields, loss_and_grad_raw,
+                  indices_to_mask)
+from .patch import patch_nn_ion, run_train_py, trainpy_patched_source
+
+__all__ = [
+    "N_THETA", "POC_TENSOR_NAMES", "TRAINPY_TENSOR_NAMES", "pack_poc", "unpack_poc", "pack_trainpy",
+    "unpack_trainpy", "FINE_TUNE_GRAD_MASK", "lib", "Handle", "PinnError", "library_path", "PinnLossPoc",
+    "PinnLossTrainPy", "loss_poc", "loss_trainpy", "fields", "loss_and_grad_raw", "indices_to_mask",
+    "patch_nn_ion", "run_train_py", "trainpy_patched_source",
+]

@@ -1,0 +1,280 @@
+// C ABI of the PINN hot path (see include/pinn_b200.h for the contract).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pinn_b200.h"
+#include "pinn_common.cuh"
+
+#include "pinn_launch.h"
+
+using namespace pinn;
+
+struct pinn_handle {
+  int device = 0;
+  int sm_count = 0;
+  Wts* wts = nullptr;              // prepared weight image
+  float* theta_dev = nullptr;      // staging for the *_host entry (1536 float)
+  double* weights_dev = nullptr;   // 3 double
+  unsigned long long* counts = nullptr;
+  double* partials = nullptr;      // [max_rows][NPART]
+  int max_rows = 0;
+  // *_host entry
+  void* stage_dev = nullptr;       // coordinates + mask
+  size_t stage_bytes = 0;
+  double* out_dev = nullptr;       // 8 sums + 1521 grads
+  double* out_pinned = nullptr;
+  float* theta_pinned = nullptr;
+  double* weights_pinned = nullptr;
+  cudaStream_t s_copy = nullptr, s_main = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  int64_t launches = 0;
+  bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::string err;
+  std::mutex mu;
+};
+
+static std::string g_create_err;
+
+static int fail(pinn_handle* h, int code, const char* what) {
+  char buf[512];
+  if (code > 0)
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString((cudaError_t)code),
+             cudaGetErrorName((cudaError_t)code));
+  else
+    snprintf(buf, sizeof(buf), "%s", what);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+#define CU(h, call)                                   \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return fail(h, (int)e__, #call); \
+  } while (0)
+
+static const int kOffsets[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
+                                 O_WGL, O_BGL, O_WG, O_BG, NTHETA};
+
+extern "C" {
+
+int pinn_version(void) { return 100; }
+int pinn_theta_size(void) { return NTHETA; }
+void pinn_theta_offsets(int* out) { memcpy(out, kOffsets, sizeof(kOffsets)); }
+
+int pinn_create(int device, pinn_handle** out) {
+  if (!out) return fail(nullptr, PINN_EINVAL, "pinn_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return fail(nullptr, (int)e, "cudaGetDeviceCount");
+  if (device < 0 || device >= ndev) return fail(nullptr, PINN_EINVAL, "pinn_create: no such CUDA device");
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, PINN_ENOTSUP, "pinn_create: this library only carries sm_100a code (B200); no fallback exists");
+  CU(nullptr, cudaSetDevice(device));
+  pinn_handle* h = new pinn_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->max_rows = h->sm_count * 8;
+  CU(h, cudaMalloc(&h->wts, sizeof(Wts)));
+  CU(h, cudaMalloc(&h->theta_dev, NPART * sizeof(float)));
+  CU(h, cudaMalloc(&h->weights_dev, 4 * sizeof(double)));
+  CU(h, cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
+  CU(h, cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
+  CU(h, cudaMalloc(&h->out_dev, NPART * sizeof(double)));
+  CU(h, cudaMallocHost(&h->out_pinned, NPART * sizeof(double)));
+  CU(h, cudaMallocHost(&h->theta_pinned, NPART * sizeof(float)));
+  CU(h, cudaMallocHost(&h->weights_pinned, 4 * sizeof(double)));
+  CU(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  CU(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+  CU(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  *out = h;
+  return 0;
+}
+
+int pinn_destroy(pinn_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->weights_dev); cudaFree(h->counts);
+  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->out_dev);
+  cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned); cudaFreeHost(h->weights_pinned);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_main) cudaStreamDestroy(h->s_main);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+const char* pinn_last_error(pinn_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int64_t pinn_launch_count(pinn_handle* h) { return h ? h->launches : 0; }
+
+int pinn_profile_begin(pinn_handle* h) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->profiling = true;
+  h->ev_used = 0;
+  return 0;
+}
+
+int pinn_profile_collect(pinn_handle* h, double* total_ms, int* launches) {
+  if (!h || !total_ms || !launches) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CU(h, cudaSetDevice(h->device));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    CU(h, cudaEventSynchronize(h->ev_pool[i + 1]));
+    float ms = 0.0f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = (int)(h->ev_used / 2);
+  h->profiling = false;
+  h->ev_used = 0;
+  return 0;
+}
+
+static int variant_coef(int variant, VariantCoef* vc, int* nev) {
+  if (variant == PINN_VARIANT_POC) { *vc = {1.0f, -0.5f, -1.0f, -1.0f}; *nev = 2; return 0; }
+  if (variant == PINN_VARIANT_TRAINPY) { *vc = {2.0f, 1.0f, 1.0f, 1.0f}; *nev = 1; return 0; }
+  return PINN_EINVAL;
+}
+
+static int grid_for(pinn_handle* h, long long n) {
+  const long long tiles = (n + 31) / 32;
+  const long long want = (tiles + step_groups() - 1) / step_groups();
+  return (int)(want < h->sm_count ? (want < 1 ? 1 : want) : h->sm_count);
+}
+
+int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                      const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
+                      uint32_t grad_mask, float bcutoff, double* sums, double* dtheta, float* E_out, void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  StepParams p{};
+  int nev = 0;
+  if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: unknown variant");
+  if (n <= 0) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: n must be positive");
+  if (!x || !y || !z || !R || !theta || !sums || !dtheta)
+    return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
+  if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
+  p.bcut = bcutoff; p.partials = h->partials; p.E_out = E_out;
+  p.base_grads = (grad_mask & 0x003Fu) != 0;
+  p.gate_grads = (grad_mask & 0xF000u) != 0;
+  CU(h, launch_prep(theta, h->wts, st));
+  h->launches++;
+  if (!weights) {
+    CU(h, launch_count(p, h->counts, h->weights_dev, st));
+    h->launches += 2;
+    weights = h->weights_dev;
+  }
+  p.weights = weights;
+  const int grid = grid_for(h, n);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling) {
+    while (h->ev_pool.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      CU(h, cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+    e0 = h->ev_pool[h->ev_used++];
+    e1 = h->ev_pool[h->ev_used++];
+    CU(h, cudaEventRecord(e0, st));
+  }
+  CU(h, launch_step(nev, true, p, grid, st));
+  if (e1) CU(h, cudaEventRecord(e1, st));
+  h->launches++;
+  CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, st));
+  h->launches++;
+  return 0;
+}
+
+int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z, const void* R,
+                int in_dtype, const float* theta, float* psi, float* lap, float* hpsi, float* res, float* E,
+                void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  StepParams p{};
+  int nev = 0;
+  if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_fields: unknown variant");
+  if (n <= 0) return fail(h, PINN_EINVAL, "pinn_fields: n must be positive");
+  if (!x || !y || !z || !R || !theta) return fail(h, PINN_EINVAL, "pinn_fields: NULL pointer argument");
+  if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_fields: bad in_dtype");
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  p.x = x; p.y = y; p.z = z; p.R = R; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
+  p.psi = psi; p.lap = lap; p.hpsi = hpsi; p.res = res; p.E_out = E;
+  CU(h, launch_prep(theta, h->wts, st));
+  CU(h, launch_step(nev, false, p, grid_for(h, n), st));
+  h->launches += 2;
+  return 0;
+}
+
+int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                           const void* R, int in_dtype, const uint8_t* mask, const double* theta_host,
+                           const double* weights_host, uint32_t grad_mask, float bcutoff, double* sums_host,
+                           double* dtheta_host, float* E_out_host) {
+  if (!h) return PINN_EINVAL;
+  if (n <= 0) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: n must be positive");
+  if (!x || !y || !z || !R || !theta_host || !sums_host || !dtheta_host)
+    return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: NULL pointer argument");
+  if (in_dtype != PINN_F32 && in_dtype != PINN_F64)
+    return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: bad in_dtype");
+  CU(h, cudaSetDevice(h->device));
+  const size_t es = in_dtype == PINN_F64 ? 8 : 4;
+  const size_t col = ((size_t)n * es + 255) & ~(size_t)255;
+  const size_t mcol = ((size_t)n + 255) & ~(size_t)255;
+  const size_t ecol = ((size_t)n * 4 + 255) & ~(size_t)255;
+  const size_t need = 4 * col + mcol + ecol;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (need > h->stage_bytes) {  // grows geometrically; steady-state steps do not allocate
+      CU(h, cudaStreamSynchronize(h->s_main));
+      if (h->stage_dev) CU(h, cudaFree(h->stage_dev));
+      h->stage_dev = nullptr;
+      const size_t cap = need + need / 4;
+      CU(h, cudaMalloc(&h->stage_dev, cap));
+      h->stage_bytes = cap;
+    }
+  }
+  char* base = (char*)h->stage_dev;
+  cudaStream_t st = h->s_main;
+  for (int i = 0; i < NTHETA; i++) h->theta_pinned[i] = (float)theta_host[i];
+  CU(h, cudaMemcpyAsync(h->theta_dev, h->theta_pinned, NTHETA * sizeof(float), cudaMemcpyHostToDevice, st));
+  const double* wdev = nullptr;
+  if (weights_host) {
+    memcpy(h->weights_pinned, weights_host, 3 * sizeof(double));
+    CU(h, cudaMemcpyAsync(h->weights_dev, h->weights_pinned, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    wdev = h->weights_dev;
+  }
+  CU(h, cudaMemcpyAsync(base + 0 * col, x, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(base + 1 * col, y, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(base + 2 * col, z, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(base + 3 * col, R, (size_t)n * es, cudaMemcpyHostToDevice, st));
+  uint8_t* mdev = nullptr;
+  if (mask) {
+    mdev = (uint8_t*)(base + 4 * col);
+    CU(h, cudaMemcpyAsync(mdev, mask, (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  float* edev = (E_out_host || true) ? (float*)(base + 4 * col + mcol) : nullptr;
+  int rc = pinn_loss_fwd_bwd(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev,
+                             h->theta_dev, wdev, grad_mask, bcutoff, h->out_dev, h->out_dev + 8, edev, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(h->out_pinned, h->out_dev, (8 + NTHETA) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  memcpy(sums_host, h->out_pinned, 8 * sizeof(double));
+  memcpy(dtheta_host, h->out_pinned + 8, NTHETA * sizeof(double));
+  return 0;
+}
+
+}  // extern "C"

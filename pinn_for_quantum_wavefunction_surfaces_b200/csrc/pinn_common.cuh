@@ -1,0 +1,49 @@
+// Shared constants and small device helpers of the PINN hot-path kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pinn {
+
+constexpr int NH = 16;   // base-MLP hidden width   (poc/main.py:227; train.py:85)
+constexpr int NE = 32;   // E-net hidden width      (poc/main.py:228; train.py:86)
+constexpr int NL = 10;   // gate hidden width       (poc/main.py:229; train.py:87)
+constexpr int NTHETA = 1521;
+constexpr int NPART = 1536;  // one row of partial sums: 1521 gradients + 8 loss sums, padded
+
+// offsets inside theta (state_dict order)
+enum : int {
+  O_W1 = 0, O_B1 = 32, O_W2 = 48, O_B2 = 304, O_WO = 320, O_BO = 336,
+  O_WE1 = 337, O_BE1 = 369, O_WE2 = 401, O_BE2 = 1425, O_WE = 1457, O_BE = 1489,
+  O_WGL = 1490, O_BGL = 1500, O_WG = 1510, O_BG = 1520,
+  // loss sums ride behind the gradients in a partial row
+  S_RES2 = 1521, S_PSI1 = 1522, S_PSI2 = 1523, S_E = 1524, S_CNT1 = 1525, S_CNT2 = 1526
+};
+
+// Weights as the kernels want them, built once per step by prep_weights_kernel and
+// bulk-copied (TMA, cp.async.bulk) into shared memory by every CTA.
+struct alignas(16) Wts {
+  float w0[NH], w1[NH], b1[NH];          // W1[:,0], W1[:,1], b1
+  float ww00[NH], ww01[NH], ww11[NH];    // w0^2, w0*w1, w1^2  (second-order channel)
+  float W2[NH * NH];                     // [j][k]  forward rows
+  float W2T[NH * NH];                    // [k][j]  reverse-sweep rows
+  float b2[NH], wo[NH];
+  float WE1[NE], bE1[NE];
+  float WE2[NE * NE];                    // [j][k]
+  float WE2T[NE * NE];                   // [k][j]
+  float bE2[NE], wE[NE];
+  float WgL[12], bgL[12], wg[12];        // 10 used
+  float bo, bE, bg, pad0;
+};
+static_assert(sizeof(Wts) % 16 == 0, "Wts must be a multiple of 16 bytes for cp.async.bulk");
+
+struct VariantCoef {  // res = cL*lap(psi) + cV*(1/r1+1/r2)*psi + cE*E*psi ; N = sN * sum(evals) + bo
+  float sN, cL, cV, cE;
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float u) {
+  // 1/(1+exp(-u)) with MUFU.EX2 + MUFU.RCP (approx, ~2 ulp); saturates correctly at +-inf
+  return __frcp_rn(1.0f + __expf(-u)) ;
+}
+
+}  // namespace pinn

@@ -1,0 +1,895 @@
+// Fused PINN residual-and-gradient kernels for B200 (sm_100a).
+//
+// What is computed (closed form of the reference's autograd path, oracle/closed_form.py):
+//   psi, lap psi, residual, loss sums and dLtot/dtheta of the parametric H2+ model
+//   (poc/main.py:247-303, 82-120, 341-355 and train.py:41-57).
+//
+// Work decomposition
+//   * a GROUP of warps owns a tile of 32 collocation points (lane = point).  The warps of a
+//     group are specialised by role: one warp per MLP evaluation of the base network
+//     (poc: (f1,f2) and the inversion image (f2,f1), poc/main.py:255-260; train.py: one)
+//     and one warp for the E(R) network + gate.  Roles meet once per tile through a
+//     shared-memory mailbox and a named barrier (forward results -> reverse-sweep seeds).
+//   * skinny layers (16x16 x 4 Taylor channels, 32x32) run as FFMA mat-vecs, weights read as
+//     broadcast LDS.128 from the shared-memory weight image that is staged ONCE per CTA
+//     with a TMA bulk copy (cp.async.bulk + mbarrier).
+//   * the weight-gradient contractions dW2 = sum_p G_p^T H_p and dWE2 = sum_p V_p^T E1_p
+//     have K = points and are dense: they run on the tensor cores (mma.sync m16n8k8
+//     TF32 with the 3xTF32 split, fp32-accurate), operands staged per warp in shared memory,
+//     accumulators persistent in registers over all tiles of the launch.
+//   * bias/vector gradients and the loss sums are reduced over the 32 points of a tile with a
+//     transposing shuffle butterfly (32 values -> one per lane).
+//   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
+//     in double precision in a fixed order (deterministic).
+#include "pinn_common.cuh"
+#include "pinn_launch.h"
+
+namespace pinn {
+
+constexpr int LDH = 72;  // row stride (floats) of the per-point stash of an MLP warp: 4 channels x 16, padded so
+                         // that both mma fragment loads (bank = 8*t + g) are conflict free
+constexpr int LDE = 40;  // row stride of the E-net warp stash (32 used)
+constexpr int EVAL_STASH = 2 * 32 * LDH;  // floats: Hs + Gs
+constexpr int ENET_STASH = 2 * 32 * LDE;  // floats: E1s + Vs
+
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigm(float u) { return rcp_approx(1.0f + __expf(-u)); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 3xTF32: x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += a*b with fp32 accuracy: big*big + big*small + small*big (small*small ~2^-22 dropped)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
+// Transposing butterfly: on entry every lane holds 32 values v[i] (its point's contribution to
+// output i); on exit the return value of lane L is sum over lanes of v[L].  31 SHFL + 31 FADD.
+template <int N>
+__device__ __forceinline__ void bfly_stage(float (&v)[32], int lane) {
+  constexpr int H = N / 2;
+  const bool up = (lane & H) != 0;
+#pragma unroll
+  for (int i = 0; i < H; i++) {
+    const float lo = v[i], hi = v[i + H];
+    const float send = up ? lo : hi;
+    const float keep = up ? hi : lo;
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+  }
+}
+__device__ __forceinline__ float bfly32(float (&v)[32], int lane) {
+  bfly_stage<32>(v, lane);
+  bfly_stage<16>(v, lane);
+  bfly_stage<8>(v, lane);
+  bfly_stage<4>(v, lane);
+  bfly_stage<2>(v, lane);
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-point geometry (poc/main.py:101-108, 269-284; train.py:41-44) and the coefficients of the
+// second-order operator D (oracle/closed_form.py:geometry)
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+  float f1, f2, ir1, ir2, al1, al2, al11, al12, al22;
+  float R;
+};
+
+__device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) {
+  float dx1, dx2, y, z, R;
+  if (p.in_f64) {
+    const double xd = ((const double*)p.x)[i], Rd = ((const double*)p.R)[i];
+    dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
+    dx2 = (float)(xd + Rd);
+    y = (float)((const double*)p.y)[i];
+    z = (float)((const double*)p.z)[i];
+    R = (float)Rd;
+  } else {
+    const float xf = ((const float*)p.x)[i];
+    R = ((const float*)p.R)[i];
+    dx1 = xf - R;
+    dx2 = xf + R;
+    y = ((const float*)p.y)[i];
+    z = ((const float*)p.z)[i];
+  }
+  Geom g;
+  const float yz = fmaf(y, y, z * z);
+  const float q1 = fmaf(dx1, dx1, yz), q2 = fmaf(dx2, dx2, yz);
+  g.ir1 = rsqrtf(q1);
+  g.ir2 = rsqrtf(q2);
+  const float r1 = q1 * g.ir1, r2 = q2 * g.ir2;
+  g.f1 = __expf(-r1);
+  g.f2 = __expf(-r2);
+  const float c12 = fmaf(dx1, dx2, yz) * g.ir1 * g.ir2;
+  g.al1 = g.f1 * fmaf(-2.0f, g.ir1, 1.0f);
+  g.al2 = g.f2 * fmaf(-2.0f, g.ir2, 1.0f);
+  g.al11 = g.f1 * g.f1;
+  g.al22 = g.f2 * g.f2;
+  g.al12 = 2.0f * g.f1 * g.f2 * c12;
+  g.R = R;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// base MLP, one evaluation at (a,b): 4-channel Taylor forward (value, d/da, d/db, D)
+//   Hs row (this lane's point): h_c[k]  at [c*16+k]   (kept for the dW2 contraction and the reverse sweep)
+//   Gs row:                     t_j, va_j, vb_j, vD_j at [c*16+j]  (overwritten by the adjoints later)
+// ---------------------------------------------------------------------------------------------
+template <bool STASH>
+__device__ __forceinline__ void mlp_forward(const Wts& w, float a, float b, float al1, float al2, float al11,
+                                            float al12, float al22, float* __restrict__ Hrow,
+                                            float* __restrict__ Grow, float& Nv, float& Dv) {
+  float h[4][NH];
+#pragma unroll
+  for (int k4 = 0; k4 < NH; k4 += 4) {
+    const float4 w0v = *reinterpret_cast<const float4*>(&w.w0[k4]);
+    const float4 w1v = *reinterpret_cast<const float4*>(&w.w1[k4]);
+    const float4 b1v = *reinterpret_cast<const float4*>(&w.b1[k4]);
+    const float4 q00 = *reinterpret_cast<const float4*>(&w.ww00[k4]);
+    const float4 q01 = *reinterpret_cast<const float4*>(&w.ww01[k4]);
+    const float4 q11 = *reinterpret_cast<const float4*>(&w.ww11[k4]);
+    const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+    const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
+    const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
+    const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = k4 + i;
+      const float u = fmaf(a, w0a[i], fmaf(b, w1a[i], b1a[i]));
+      const float s = sigm(u);
+      const float sp = fmaf(-s, s, s);             // s(1-s)
+      const float spp = fmaf(-2.0f * s, sp, sp);   // s'(1-2s)
+      const float d1 = fmaf(al1, w0a[i], al2 * w1a[i]);
+      const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
+      h[0][k] = s;
+      h[1][k] = sp * w0a[i];
+      h[2][k] = sp * w1a[i];
+      h[3][k] = fmaf(sp, d1, spp * q);
+    }
+  }
+  if (STASH) {
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int k4 = 0; k4 < NH; k4 += 4)
+        *reinterpret_cast<float4*>(&Hrow[c * NH + k4]) = make_float4(h[c][k4], h[c][k4 + 1], h[c][k4 + 2], h[c][k4 + 3]);
+  }
+  float accN = 0.0f, accD = 0.0f;
+#pragma unroll
+  for (int j4 = 0; j4 < NH; j4 += 4) {
+    float tt[4], va[4], vb[4], vD[4];
+    const float4 b2v = *reinterpret_cast<const float4*>(&w.b2[j4]);
+    const float4 wov = *reinterpret_cast<const float4*>(&w.wo[j4]);
+    const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = j4 + i;
+      float v0 = b2a[i], v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#pragma unroll
+      for (int k4 = 0; k4 < NH; k4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w.W2[j * NH + k4]);
+        const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          v0 = fmaf(wa[kk], h[0][k4 + kk], v0);
+          v1 = fmaf(wa[kk], h[1][k4 + kk], v1);
+          v2 = fmaf(wa[kk], h[2][k4 + kk], v2);
+          v3 = fmaf(wa[kk], h[3][k4 + kk], v3);
+        }
+      }
+      const float t = sigm(v0);
+      const float tp = fmaf(-t, t, t);
+      const float tpp = fmaf(-2.0f * t, tp, tp);
+      const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
+      const float gD = fmaf(tp, v3, tpp * Q);
+      accN = fmaf(woa[i], t, accN);
+      accD = fmaf(woa[i], gD, accD);
+      tt[i] = t; va[i] = v1; vb[i] = v2; vD[i] = v3;
+    }
+    if (STASH) {
+      *reinterpret_cast<float4*>(&Grow[0 * NH + j4]) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+      *reinterpret_cast<float4*>(&Grow[1 * NH + j4]) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(&Grow[2 * NH + j4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+      *reinterpret_cast<float4*>(&Grow[3 * NH + j4]) = make_float4(vD[0], vD[1], vD[2], vD[3]);
+    }
+  }
+  Nv = accN;
+  Dv = accD;
+}
+
+// persistent per-lane accumulators of an MLP warp
+struct MlpAcc {
+  float cW2[2][4];   // mma C fragments of dW2 (16x16): n-tile 0/1
+  float s0, s1;      // butterfly chunks: {dwo[16], db2[16]}, {dw0[16], dw1[16]}
+  double s2;         // {db1[16], loss sums (role 0)}: double because the loss sums ride here
+};
+
+// Reverse sweep of one MLP evaluation for the seeds lamN = dL/dNv, lamD = dL/dDv
+// (oracle/closed_form.py:mlp_bwd).  `extra` are 16 more per-point values reduced with db1.
+__device__ __forceinline__ void mlp_backward(const Wts& w, float a, float b, float al1, float al2, float al11,
+                                             float al12, float al22, float lamN, float lamD,
+                                             float* __restrict__ Hs, float* __restrict__ Gs, int lane,
+                                             const float (&extra)[16], MlpAcc& acc) {
+  float* Hrow = Hs + lane * LDH;
+  float* Grow = Gs + lane * LDH;
+  float vbar[4][NH];
+  float ch0[32];  // dwo | db2
+#pragma unroll
+  for (int j4 = 0; j4 < NH; j4 += 4) {
+    const float4 tv = *reinterpret_cast<const float4*>(&Grow[0 * NH + j4]);
+    const float4 av = *reinterpret_cast<const float4*>(&Grow[1 * NH + j4]);
+    const float4 bv = *reinterpret_cast<const float4*>(&Grow[2 * NH + j4]);
+    const float4 dv = *reinterpret_cast<const float4*>(&Grow[3 * NH + j4]);
+    const float4 wov = *reinterpret_cast<const float4*>(&w.wo[j4]);
+    const float ta[4] = {tv.x, tv.y, tv.z, tv.w}, vaa[4] = {av.x, av.y, av.z, av.w};
+    const float vba[4] = {bv.x, bv.y, bv.z, bv.w}, vDa[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float woa[4] = {wov.x, wov.y, wov.z, wov.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = j4 + i;
+      const float t = ta[i], v1 = vaa[i], v2 = vba[i], v3 = vDa[i];
+      const float tp = fmaf(-t, t, t);
+      const float tpp = fmaf(-2.0f * t, tp, tp);
+      const float tppp = tp * fmaf(-6.0f, tp, 1.0f);
+      const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
+      const float gD = fmaf(tp, v3, tpp * Q);
+      const float tbar = lamN * woa[i], gDbar = lamD * woa[i];
+      ch0[j] = fmaf(lamN, t, lamD * gD);
+      const float c2 = gDbar * tpp;
+      vbar[3][j] = gDbar * tp;
+      vbar[1][j] = c2 * fmaf(2.0f * al11, v1, al12 * v2);
+      vbar[2][j] = c2 * fmaf(al12, v1, 2.0f * al22 * v2);
+      vbar[0][j] = fmaf(tbar, tp, gDbar * fmaf(tpp, v3, tppp * Q));
+      ch0[16 + j] = vbar[0][j];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int j4 = 0; j4 < NH; j4 += 4)
+      *reinterpret_cast<float4*>(&Grow[c * NH + j4]) =
+          make_float4(vbar[c][j4], vbar[c][j4 + 1], vbar[c][j4 + 2], vbar[c][j4 + 3]);
+  __syncwarp();
+
+  // ---- dW2[j][k] += sum_{p,c} G[p][c][j] * H[p][c][k] on the tensor cores (3xTF32) ----
+  {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int po = 0; po < 4; po++) {
+        const float* Ga = Gs + (po * 8 + t) * LDH + c * NH;
+        const float* Gb = Ga + 4 * LDH;
+        const float* Ha = Hs + (po * 8 + t) * LDH + c * NH;
+        const float* Hb = Ha + 4 * LDH;
+        uint32_t ah[4], al[4];
+        split_tf32(Ga[g], ah[0], al[0]);
+        split_tf32(Ga[g + 8], ah[1], al[1]);
+        split_tf32(Gb[g], ah[2], al[2]);
+        split_tf32(Gb[g + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(Ha[nt * 8 + g], bh0, bl0);
+          split_tf32(Hb[nt * 8 + g], bh1, bl1);
+          mma_3xtf32(acc.cW2[nt], ah, al, bh0, bh1, bl0, bl1);
+        }
+      }
+    }
+  }
+  acc.s0 += bfly32(ch0, lane);
+
+  // ---- hbar = W2^T vbar, then layer-1 reverse sweep neuron by neuron ----
+  float ch1[32], ch2[32];
+#pragma unroll
+  for (int k4 = 0; k4 < NH; k4 += 4) {
+    const float4 sv = *reinterpret_cast<const float4*>(&Hrow[k4]);  // h channel 0 = s_k
+    const float4 w0v = *reinterpret_cast<const float4*>(&w.w0[k4]);
+    const float4 w1v = *reinterpret_cast<const float4*>(&w.w1[k4]);
+    const float4 q00 = *reinterpret_cast<const float4*>(&w.ww00[k4]);
+    const float4 q01 = *reinterpret_cast<const float4*>(&w.ww01[k4]);
+    const float4 q11 = *reinterpret_cast<const float4*>(&w.ww11[k4]);
+    const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+    const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+    const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
+    const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = k4 + i;
+      float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < NH; j4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w.W2T[k * NH + j4]);
+        const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          h0 = fmaf(wa[jj], vbar[0][j4 + jj], h0);
+          h1 = fmaf(wa[jj], vbar[1][j4 + jj], h1);
+          h2 = fmaf(wa[jj], vbar[2][j4 + jj], h2);
+          h3 = fmaf(wa[jj], vbar[3][j4 + jj], h3);
+        }
+      }
+      const float s = sa[i], w0 = w0a[i], w1 = w1a[i];
+      const float sp = fmaf(-s, s, s);
+      const float spp = fmaf(-2.0f * s, sp, sp);
+      const float sppp = sp * fmaf(-6.0f, sp, 1.0f);
+      const float d1 = fmaf(al1, w0, al2 * w1);
+      const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
+      const float ubar = fmaf(h0, sp, fmaf(fmaf(h1, w0, fmaf(h2, w1, h3 * d1)), spp, h3 * q * sppp));
+      ch1[k] = fmaf(h1, sp, fmaf(h3, fmaf(sp, al1, spp * fmaf(2.0f * al11, w0, al12 * w1)), ubar * a));
+      ch1[16 + k] = fmaf(h2, sp, fmaf(h3, fmaf(sp, al2, spp * fmaf(al12, w0, 2.0f * al22 * w1)), ubar * b));
+      ch2[k] = ubar;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) ch2[16 + i] = extra[i];
+  acc.s1 += bfly32(ch1, lane);
+  acc.s2 += (double)bfly32(ch2, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// E(R) network (poc/main.py:249-253; train.py:50-52) and gate (poc/main.py:262-264; train.py:48-49)
+// ---------------------------------------------------------------------------------------------
+template <bool STASH>
+__device__ __forceinline__ float enet_forward(const Wts& w, float R, float* __restrict__ E1row,
+                                              float* __restrict__ Vrow) {
+  float e1[NE];
+#pragma unroll
+  for (int k4 = 0; k4 < NE; k4 += 4) {
+    const float4 wv = *reinterpret_cast<const float4*>(&w.WE1[k4]);
+    const float4 bv = *reinterpret_cast<const float4*>(&w.bE1[k4]);
+    e1[k4 + 0] = sigm(fmaf(R, wv.x, bv.x));
+    e1[k4 + 1] = sigm(fmaf(R, wv.y, bv.y));
+    e1[k4 + 2] = sigm(fmaf(R, wv.z, bv.z));
+    e1[k4 + 3] = sigm(fmaf(R, wv.w, bv.w));
+    if (STASH) *reinterpret_cast<float4*>(&E1row[k4]) = make_float4(e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
+  }
+  float E = w.bE;
+#pragma unroll
+  for (int j4 = 0; j4 < NE; j4 += 4) {
+    const float4 b2v = *reinterpret_cast<const float4*>(&w.bE2[j4]);
+    const float4 wEv = *reinterpret_cast<const float4*>(&w.wE[j4]);
+    const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
+    float e2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = j4 + i;
+      float v0 = b2a[i], v1 = 0.0f;  // two partial sums for ILP
+#pragma unroll
+      for (int k4 = 0; k4 < NE; k4 += 8) {
+        const float4 wa = *reinterpret_cast<const float4*>(&w.WE2[j * NE + k4]);
+        const float4 wb = *reinterpret_cast<const float4*>(&w.WE2[j * NE + k4 + 4]);
+        v0 = fmaf(wa.x, e1[k4 + 0], v0); v0 = fmaf(wa.y, e1[k4 + 1], v0);
+        v0 = fmaf(wa.z, e1[k4 + 2], v0); v0 = fmaf(wa.w, e1[k4 + 3], v0);
+        v1 = fmaf(wb.x, e1[k4 + 4], v1); v1 = fmaf(wb.y, e1[k4 + 5], v1);
+        v1 = fmaf(wb.z, e1[k4 + 6], v1); v1 = fmaf(wb.w, e1[k4 + 7], v1);
+      }
+      e2[i] = sigm(v0 + v1);
+      E = fmaf(wEa[i], e2[i], E);
+    }
+    if (STASH) *reinterpret_cast<float4*>(&Vrow[j4]) = make_float4(e2[0], e2[1], e2[2], e2[3]);
+  }
+  return E;
+}
+
+__device__ __forceinline__ float gate_forward(const Wts& w, float R) {
+  float g = w.bg;
+#pragma unroll
+  for (int i = 0; i < NL; i++) g = fmaf(w.wg[i], sigm(fmaf(R, w.WgL[i], w.bgL[i])), g);
+  return g;
+}
+
+struct EnetAcc {
+  float cWE2[2][4][4];         // mma C fragments of dWE2 (32x32): [m-tile][n-tile]
+  float s0, s1, s2, s3, s4;    // butterfly chunks: dwE, dbE2, dWE1, dbE1, {dWgL,dbgL,dwg,dbg,dbE}
+};
+
+// Reverse sweep of the E-net and gate for the seeds Ebar = dL/dE, gbar = dL/dgate.
+__device__ __forceinline__ void enet_backward(const Wts& w, float R, float Ebar, float gbar, bool gate_grads,
+                                              float* __restrict__ E1s, float* __restrict__ Vs, int lane,
+                                              EnetAcc& acc) {
+  float* E1row = E1s + lane * LDE;
+  float* Vrow = Vs + lane * LDE;
+  float vbar[NE];
+  {
+    float ch[32];
+#pragma unroll
+    for (int j4 = 0; j4 < NE; j4 += 4) {
+      const float4 ev = *reinterpret_cast<const float4*>(&Vrow[j4]);
+      const float4 wEv = *reinterpret_cast<const float4*>(&w.wE[j4]);
+      const float ea[4] = {ev.x, ev.y, ev.z, ev.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ch[j4 + i] = Ebar * ea[i];
+        vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
+      }
+      *reinterpret_cast<float4*>(&Vrow[j4]) = make_float4(vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
+    }
+    acc.s0 += bfly32(ch, lane);
+  }
+  __syncwarp();
+  // ---- dWE2[j][k] += sum_p V[p][j] * E1[p][k] on the tensor cores (3xTF32) ----
+  {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const float* Va = Vs + (ks * 8 + t) * LDE;
+      const float* Vb = Va + 4 * LDE;
+      const float* Ea = E1s + (ks * 8 + t) * LDE;
+      const float* Eb = Ea + 4 * LDE;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        split_tf32(Va[mt * 16 + g], ah[mt][0], al[mt][0]);
+        split_tf32(Va[mt * 16 + g + 8], ah[mt][1], al[mt][1]);
+        split_tf32(Vb[mt * 16 + g], ah[mt][2], al[mt][2]);
+        split_tf32(Vb[mt * 16 + g + 8], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Ea[nt * 8 + g], bh0, bl0);
+        split_tf32(Eb[nt * 8 + g], bh1, bl1);
+        mma_3xtf32(acc.cWE2[0][nt], ah[0], al[0], bh0, bh1, bl0, bl1);
+        mma_3xtf32(acc.cWE2[1][nt], ah[1], al[1], bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  {
+    float ch[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) ch[i] = vbar[i];
+    acc.s1 += bfly32(ch, lane);
+  }
+  // ---- e1bar = WE2^T vbar, layer-1 reverse sweep ----
+  {
+    float chW[32], chB[32];
+#pragma unroll
+    for (int k4 = 0; k4 < NE; k4 += 4) {
+      const float4 ev = *reinterpret_cast<const float4*>(&E1row[k4]);
+      const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int k = k4 + i;
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < NE; j4 += 8) {
+          const float4 wa = *reinterpret_cast<const float4*>(&w.WE2T[k * NE + j4]);
+          const float4 wb = *reinterpret_cast<const float4*>(&w.WE2T[k * NE + j4 + 4]);
+          s0 = fmaf(wa.x, vbar[j4 + 0], s0); s0 = fmaf(wa.y, vbar[j4 + 1], s0);
+          s0 = fmaf(wa.z, vbar[j4 + 2], s0); s0 = fmaf(wa.w, vbar[j4 + 3], s0);
+          s1 = fmaf(wb.x, vbar[j4 + 4], s1); s1 = fmaf(wb.y, vbar[j4 + 5], s1);
+          s1 = fmaf(wb.z, vbar[j4 + 6], s1); s1 = fmaf(wb.w, vbar[j4 + 7], s1);
+        }
+        const float ub = (s0 + s1) * fmaf(-ea[i], ea[i], ea[i]);
+        chW[k] = ub * R;
+        chB[k] = ub;
+      }
+    }
+    acc.s2 += bfly32(chW, lane);
+    acc.s3 += bfly32(chB, lane);
+  }
+  // ---- gate reverse sweep + dbE ----
+  {
+    float ch[32];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const float s = sigm(fmaf(R, w.WgL[i], w.bgL[i]));
+      const float ub = gate_grads ? gbar * w.wg[i] * fmaf(-s, s, s) : 0.0f;
+      ch[i] = ub * R;
+      ch[10 + i] = ub;
+      ch[20 + i] = gate_grads ? gbar * s : 0.0f;
+    }
+    ch[30] = gate_grads ? gbar : 0.0f;
+    ch[31] = Ebar;
+    acc.s4 += bfly32(ch, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel.  NEV = MLP evaluations per point (2: poc, 1: train.py); TRAIN = with reverse sweep
+// ---------------------------------------------------------------------------------------------
+template <int NEV>
+__host__ __device__ constexpr int group_stash_floats() { return NEV * EVAL_STASH + ENET_STASH; }
+
+template <int NEV, int G>
+__host__ __device__ constexpr size_t step_smem_bytes() {
+  return sizeof(Wts) + 16 /*mbarrier*/ + sizeof(float2) * G * 2 * 3 * 32 + sizeof(float) * G * group_stash_floats<NEV>();
+}
+
+template <int NEV, int G, bool TRAIN>
+__global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const StepParams p) {
+  constexpr int WPG = NEV + 1;  // warps per group
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Wts& w = *reinterpret_cast<Wts*>(smem_raw);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Wts));
+  float2* mbox = reinterpret_cast<float2*>(smem_raw + sizeof(Wts) + 16);
+  float* stash = reinterpret_cast<float*>(smem_raw + sizeof(Wts) + 16 + sizeof(float2) * G * 2 * 3 * 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = warp / WPG, role = warp % WPG;  // role < NEV: MLP evaluation; role == NEV: E-net + gate
+  const bool is_mlp = role < NEV;
+
+  // ---- stage the weight image once per CTA: TMA bulk copy global -> shared, completion on an mbarrier ----
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                 "r"((uint32_t)sizeof(Wts))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&w)),
+        "l"(p.wts), "r"((uint32_t)sizeof(Wts)), "r"(smem_u32(mbar))
+        : "memory");
+  }
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(mbar))
+          : "memory");
+    }
+  }
+
+  float* gstash = stash + grp * group_stash_floats<NEV>();
+  float* Hs = gstash + (is_mlp ? role * EVAL_STASH : NEV * EVAL_STASH);
+  float* Gs = Hs + (is_mlp ? 32 * LDH : 32 * LDE);  // for the E-net warp: Hs = E1s, Gs = Vs
+  float2* gbox = mbox + grp * (2 * 3 * 32);
+
+  double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
+  if (TRAIN) { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
+  const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
+  const float sN = p.vc.sN, cL = p.vc.cL, cV = p.vc.cV, cE = p.vc.cE;
+
+  MlpAcc macc;
+  EnetAcc eacc;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) macc.cW2[i][j] = 0.0f;
+  macc.s0 = macc.s1 = 0.0f; macc.s2 = 0.0;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) eacc.cWE2[a][b][c] = 0.0f;
+  eacc.s0 = eacc.s1 = eacc.s2 = eacc.s3 = eacc.s4 = 0.0f;
+
+  const long long ntiles = (p.n + 31) >> 5;
+  const long long tstride = (long long)gridDim.x * G;
+  int it = 0;
+  for (long long tile = (long long)blockIdx.x * G + grp; tile < ntiles; tile += tstride, ++it) {
+    const long long pidx = tile * 32 + lane;
+    const bool valid = pidx < p.n;
+    const long long pi = valid ? pidx : (p.n - 1);
+    const Geom g = load_geom(p, pi);
+    float2* box = gbox + (it & 1) * (3 * 32);
+
+    // the evaluation at the inversion image swaps the roles of the two nuclei (poc/main.py:255-256)
+    const bool sw = (role == 1) && is_mlp;
+    const float a = sw ? g.f2 : g.f1, b = sw ? g.f1 : g.f2;
+    const float al1 = sw ? g.al2 : g.al1, al2 = sw ? g.al1 : g.al2;
+    const float al11 = sw ? g.al22 : g.al11, al22 = sw ? g.al11 : g.al22;
+    const float al12 = g.al12;
+
+    if (is_mlp) {
+      float Nv, Dv;
+      mlp_forward<TRAIN>(w, a, b, al1, al2, al11, al12, al22, Hs + lane * LDH, Gs + lane * LDH, Nv, Dv);
+      box[role * 32 + lane] = make_float2(Nv, Dv);
+    } else {
+      const float E = enet_forward<TRAIN>(w, g.R, Hs + lane * LDE, Gs + lane * LDE);
+      const float gt = gate_forward(w, g.R);
+      box[2 * 32 + lane] = make_float2(E, gt);
+    }
+    named_barrier(1 + grp, WPG * 32);
+
+    // ---- combine (every role recomputes the few scalars it needs) ----
+    float2 m0 = box[lane];
+    if (NEV == 2) { const float2 m1 = box[32 + lane]; m0.x += m1.x; m0.y += m1.y; }
+    const float2 me = box[2 * 32 + lane];
+    const float E = me.x, gate = me.y;
+    const float N = fmaf(sN, m0.x, w.bo), DN = sN * m0.y;
+    const float q = g.ir1 + g.ir2;
+    const float fs = g.f1 + g.f2;
+    const float psi = fmaf(gate, N, fs);
+    const float lcao = fmaf(cL, fs, fmaf(cV - 2.0f * cL, fmaf(g.f1, g.ir1, g.f2 * g.ir2),
+                                          cV * fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+    const float inner = fmaf(cL, DN, cV * q * N);
+    const float res = fmaf(gate, inner, fmaf(cE * E, psi, lcao));
+
+    if (!TRAIN) {
+      if (valid) {
+        if (role == 0) {
+          if (p.psi) p.psi[pidx] = psi;
+          if (p.lap) p.lap[pidx] = g.al1 + g.al2 + gate * DN;
+          if (p.res) p.res[pidx] = res;
+          if (p.hpsi)
+            p.hpsi[pidx] = fmaf(gate, fmaf(-0.5f, DN, -q * N),
+                                fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+        } else if (!is_mlp) {
+          if (p.E_out) p.E_out[pidx] = E;
+        }
+      }
+      continue;
+    }
+
+    // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
+    float m1f, m2f;
+    if (p.mask) {
+      const unsigned mk = p.mask[pi];
+      m1f = (mk & 1u) ? 1.0f : 0.0f;
+      m2f = (mk & 2u) ? 1.0f : 0.0f;
+    } else {
+      m1f = (g.ir1 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+      m2f = (g.ir2 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+    }
+    const float vw = valid ? 1.0f : 0.0f;
+    const float rbar = 2.0f * w_pde * res * vw;
+    const float pbar = 2.0f * fmaf(w_bc1, m1f, w_bc2 * m2f) * psi * vw;
+    if (is_mlp) {
+      const float lamN = fmaf(rbar, gate * fmaf(cV, q, cE * E), pbar * gate);
+      const float lamD = rbar * cL * gate;
+      float extra[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) extra[i] = 0.0f;
+      if (role == 0) {
+        extra[0] = res * res * vw;
+        extra[1] = psi * psi * m1f * vw;
+        extra[2] = psi * psi * m2f * vw;
+        extra[3] = E * vw;
+        extra[4] = p.base_grads ? lamN : 0.0f;  // dL/dbo
+        extra[5] = m1f * vw;
+        extra[6] = m2f * vw;
+      }
+      if (p.base_grads) {
+        mlp_backward(w, a, b, al1, al2, al11, al12, al22, sN * lamN, sN * lamD, Hs, Gs, lane, extra, macc);
+      } else if (role == 0) {
+        float ch[32];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { ch[i] = 0.0f; ch[16 + i] = extra[i]; }
+        macc.s2 += (double)bfly32(ch, lane);
+      }
+    } else {
+      if (valid && p.E_out) p.E_out[pidx] = E;
+      const float gbar = fmaf(rbar, fmaf(cE * E, N, inner), pbar * N);
+      const float Ebar = rbar * cE * psi;
+      enet_backward(w, g.R, Ebar, gbar, p.gate_grads != 0, Hs, Gs, lane, eacc);
+    }
+  }
+
+  if (!TRAIN) return;
+
+  // ---- fold the per-warp accumulators into one row per CTA (fixed order -> deterministic) ----
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(stash);  // NPART doubles, reuses the stash
+  for (int i = tid; i < NPART; i += blockDim.x) red[i] = 0.0;
+  __syncthreads();
+  const int nwarps = WPG * G;
+  for (int wv = 0; wv < nwarps; wv++) {
+    if (warp == wv) {
+      const int gq = lane >> 2, tq = lane & 3;
+      if (is_mlp) {
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          red[O_W2 + gq * NH + nt * 8 + 2 * tq] += macc.cW2[nt][0];
+          red[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] += macc.cW2[nt][1];
+          red[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] += macc.cW2[nt][2];
+          red[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] += macc.cW2[nt][3];
+        }
+        red[lane < 16 ? O_WO + lane : O_B2 + lane - 16] += macc.s0;
+        red[lane < 16 ? O_W1 + 2 * lane : O_W1 + 2 * (lane - 16) + 1] += macc.s1;
+        if (lane < 16) red[O_B1 + lane] += macc.s2;
+        else if (role == 0) {
+          const int e = lane - 16;
+          const int dst = e == 0 ? S_RES2 : e == 1 ? S_PSI1 : e == 2 ? S_PSI2 : e == 3 ? S_E
+                        : e == 4 ? O_BO : e == 5 ? S_CNT1 : e == 6 ? S_CNT2 : -1;
+          if (dst >= 0) red[dst] += macc.s2;
+        }
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int j = mt * 16 + gq, k = nt * 8 + 2 * tq;
+            red[O_WE2 + j * NE + k] += eacc.cWE2[mt][nt][0];
+            red[O_WE2 + j * NE + k + 1] += eacc.cWE2[mt][nt][1];
+            red[O_WE2 + (j + 8) * NE + k] += eacc.cWE2[mt][nt][2];
+            red[O_WE2 + (j + 8) * NE + k + 1] += eacc.cWE2[mt][nt][3];
+          }
+        red[O_WE + lane] += eacc.s0;
+        red[O_BE2 + lane] += eacc.s1;
+        red[O_WE1 + lane] += eacc.s2;
+        red[O_BE1 + lane] += eacc.s3;
+        const int dst = lane < 10 ? O_WGL + lane : lane < 20 ? O_BGL + lane - 10 : lane < 30 ? O_WG + lane - 20
+                      : lane == 30 ? O_BG : O_BE;
+        red[dst] += eacc.s4;
+      }
+    }
+    __syncthreads();
+  }
+  double* row = p.partials + (size_t)blockIdx.x * NPART;
+  for (int i = tid; i < NPART; i += blockDim.x) row[i] = red[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta -> Wts image
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_weights_kernel(const float* __restrict__ th, Wts* __restrict__ out) {
+  const int t = threadIdx.x;
+  for (int i = t; i < NH; i += blockDim.x) {
+    const float a = th[O_W1 + 2 * i], b = th[O_W1 + 2 * i + 1];
+    out->w0[i] = a; out->w1[i] = b; out->b1[i] = th[O_B1 + i];
+    out->ww00[i] = a * a; out->ww01[i] = a * b; out->ww11[i] = b * b;
+    out->b2[i] = th[O_B2 + i]; out->wo[i] = th[O_WO + i];
+  }
+  for (int i = t; i < NH * NH; i += blockDim.x) {
+    const int j = i / NH, k = i % NH;
+    out->W2[i] = th[O_W2 + i];
+    out->W2T[k * NH + j] = th[O_W2 + i];
+  }
+  for (int i = t; i < NE; i += blockDim.x) {
+    out->WE1[i] = th[O_WE1 + i]; out->bE1[i] = th[O_BE1 + i];
+    out->bE2[i] = th[O_BE2 + i]; out->wE[i] = th[O_WE + i];
+  }
+  for (int i = t; i < NE * NE; i += blockDim.x) {
+    const int j = i / NE, k = i % NE;
+    out->WE2[i] = th[O_WE2 + i];
+    out->WE2T[k * NE + j] = th[O_WE2 + i];
+  }
+  for (int i = t; i < 12; i += blockDim.x) {
+    const bool in = i < NL;
+    out->WgL[i] = in ? th[O_WGL + i] : 0.0f;
+    out->bgL[i] = in ? th[O_BGL + i] : 0.0f;
+    out->wg[i] = in ? th[O_WG + i] : 0.0f;
+  }
+  if (t == 0) { out->bo = th[O_BO]; out->bE = th[O_BE]; out->bg = th[O_BG]; out->pad0 = 0.0f; }
+}
+
+// counts of the two boundary sets -> weights {1/n, 1/cnt1, 1/cnt2} (only when the caller passes no weights)
+__global__ void count_sets_kernel(const StepParams p, unsigned long long* counts) {
+  unsigned c1 = 0, c2 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    if (p.mask) {
+      const unsigned mk = p.mask[i];
+      c1 += mk & 1u; c2 += (mk >> 1) & 1u;
+    } else {
+      const Geom g = load_geom(p, i);
+      c1 += (g.ir1 * p.bcut <= 1.0f); c2 += (g.ir2 * p.bcut <= 1.0f);
+    }
+  }
+  c1 = __reduce_add_sync(0xffffffffu, c1);
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&counts[0], c1); atomicAdd(&counts[1], c2); }
+}
+__global__ void weights_from_counts_kernel(const unsigned long long* counts, long long n, double* w) {
+  w[0] = 1.0 / (double)n;
+  w[1] = 1.0 / (double)counts[0];  // empty set -> inf -> NaN loss, like the reference's mean over an empty selection
+  w[2] = 1.0 / (double)counts[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// add the partial rows (fixed order, double) -> dtheta, sums
+// block = 256 threads = 32 entries x 8 row-slices
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
+                                                              const double* __restrict__ weights, uint32_t grad_mask,
+                                                              double* __restrict__ dtheta, double* __restrict__ sums,
+                                                              const float* __restrict__ E_out, long long n) {
+  __shared__ double sh[8][33];
+  __shared__ double tot[32];
+  const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + e;
+  double s = 0.0;
+  for (int r = sl; r < nrows; r += 8) s += partials[(size_t)r * NPART + idx];
+  sh[sl][e] = s;
+  __syncthreads();
+  if (sl == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sh[i][e];
+    tot[e] = t;
+    if (idx < NTHETA) {
+      // tensor index of this scalar -> honour grad_mask
+      const int offs[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
+                            O_WGL, O_BGL, O_WG, O_BG, NTHETA};
+      int ti = 0;
+#pragma unroll
+      for (int k = 1; k < 16; k++) ti += (idx >= offs[k]);
+      dtheta[idx] = ((grad_mask >> ti) & 1u) ? t : 0.0;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == (S_RES2 / 32) && threadIdx.x == 0) {
+    const int b = S_RES2 - (S_RES2 / 32) * 32;
+    const double r2 = tot[b], p1 = tot[b + 1], p2 = tot[b + 2], sE = tot[b + 3];
+    const double Lpde = weights[0] * r2, Lbc = weights[1] * p1 + weights[2] * p2;
+    sums[0] = Lpde + Lbc; sums[1] = Lpde; sums[2] = Lbc; sums[3] = sE;
+    sums[4] = r2; sums[5] = p1; sums[6] = p2;
+    sums[7] = (E_out && n > 0) ? (double)E_out[n - 1] : 0.0;
+  }
+}
+
+}  // namespace pinn
+
+// =================================================================================================
+// host-side launchers used by pinn_capi.cu
+// =================================================================================================
+namespace pinn {
+
+template <int NEV, int G, bool TRAIN>
+static cudaError_t launch_step_t(const StepParams& p, int grid, cudaStream_t st) {
+  auto kern = pinn_step_kernel<NEV, G, TRAIN>;
+  constexpr size_t smem = step_smem_bytes<NEV, G>();
+  static bool configured[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  kern<<<grid, (NEV + 1) * 32 * G, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+constexpr int GROUPS = 4;
+
+cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
+  if (nev == 2) return train ? launch_step_t<2, GROUPS, true>(p, grid, st) : launch_step_t<2, GROUPS, false>(p, grid, st);
+  return train ? launch_step_t<1, GROUPS, true>(p, grid, st) : launch_step_t<1, GROUPS, false>(p, grid, st);
+}
+int step_groups() { return GROUPS; }
+
+cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st) {
+  prep_weights_kernel<<<1, 256, 0, st>>>(theta, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  count_sets_kernel<<<296, 256, 0, st>>>(p, counts);
+  weights_from_counts_kernel<<<1, 1, 0, st>>>(counts, p.n, weights);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
+                          double* sums, const float* E_out, long long n, cudaStream_t st) {
+  reduce_partials_kernel<<<NPART / 32, 256, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace pinn

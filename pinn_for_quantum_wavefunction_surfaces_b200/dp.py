@@ -1,0 +1,48 @@
+"""Data-parallel step: collocation points shard across ranks, one small all-reduce.
+
+Each rank evaluates its shard with the GLOBAL weights {1/n, 1/|set1|, 1/|set2|}, so the shard
+results (loss terms, sums, dLtot/dtheta) simply add; one ``all_reduce(SUM)`` over a fused
+float64 buffer of 8 + 1521 scalars finishes the step.  The global set sizes come from one tiny
+all-reduce of the local counts (or from the caller, who usually knows them from the sampler).
+No other collective exists on this path: the model has 1521 parameters, so replicas + point sharding
+is the only parallelism.
+"""
+import torch
+import torch.distributed as dist
+
+from . import params as P
+
+N_OUT = 8 + P.N_THETA
+
+
+def global_weights(n_local, c1_local, c2_local, group=None, device="cpu"):
+    """All-reduce the local point/set counts -> float64 tensor {1/n, 1/c1, 1/c2} (global)."""
+    c = torch.tensor([float(n_local), float(c1_local), float(c2_local)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / c
+
+
+def dp_loss_and_grad(local_step, weights, group=None, out=None):
+    """Run `local_step(weights, out)` on this rank's shard and all-reduce the fused result.
+
+    local_step must fill `out` (float64, 8+1521: sums then dLtot/dtheta) for the shard using the global
+    `weights`.  On the GPU path it is a closure over ``ops.loss_and_grad_raw`` writing into views of `out`;
+    CPU tests inject the oracle.  Returns (sums[8], dtheta[1521]) views of the reduced buffer; sums[7]
+    (E of the last point) is rank-local information and is meaningless after the reduction."""
+    if out is None:
+        out = torch.empty(N_OUT, dtype=torch.float64, device=weights.device)
+    local_step(weights, out)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out[:8], out[8:]
+
+
+def make_gpu_local_step(variant, x, y, z, R, theta, mask=None, grad_mask=0xFFFF):
+    """Closure for dp_loss_and_grad on CUDA shards (tensors as in ops.loss_and_grad_raw)."""
+    from . import ops
+
+    def step(weights, out):
+        ops.loss_and_grad_raw(variant, x, y, z, R, theta, mask, weights, grad_mask, sums=out[:8], dtheta=out[8:])
+
+    return step

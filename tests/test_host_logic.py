@@ -1,0 +1,180 @@
+"""CPU-only tests: C-ABI exports, parameter packing, the train.py/NN_ion seams, data-parallel algebra."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pinn_for_quantum_wavefunction_surfaces_b200 as pk
+from pinn_for_quantum_wavefunction_surfaces_b200 import params as P
+from oracle import closed_form as cf
+from oracle import layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    return g.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "pinn_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pinn_[a-z_0-9]+)\s*\(", hdr)) - {"pinn_handle"})
+    assert len(declared) >= 12
+    L = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.pinn_version() >= 100 and L.pinn_theta_size() == 1521
+    offs = (ctypes.c_int * 17)()
+    L.pinn_theta_offsets(offs)
+    assert list(offs) == layout.offsets() + [1521]
+    assert sorted(declared) == sorted(set(pk._lib.EXPORTS)), "ctypes binding and header disagree"
+
+
+def test_no_cpu_fallback(built):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pk.PinnError):
+        pk.Handle(0)
+    x = torch.zeros(8, 1, dtype=torch.float64)
+    with pytest.raises(pk.PinnError):
+        pk.fields("poc", x, x, x, x + 1, torch.zeros(1521))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pinn_for_quantum_wavefunction_surfaces_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle[/.](closed_form|ref_autograd|layout)",
+                                     src, re.M), f
+
+
+def test_param_packing_matches_oracle_layout():
+    rng = np.random.default_rng(0)
+    theta = rng.standard_normal(1521)
+    tp = [torch.tensor(a) for a in layout.to_trainpy(theta)]
+    assert np.array_equal(P.pack_trainpy(tp, dtype=torch.float64).numpy(), theta)
+    back = P.unpack_trainpy(torch.tensor(theta))
+    for a, b in zip(back, tp):
+        assert a.shape == b.shape and torch.equal(a, b)
+    poc = [torch.tensor(a) for a in layout.unpack_poc(theta)]
+    assert np.array_equal(P.pack_poc(poc, dtype=torch.float64).numpy(), theta)
+    ps = [torch.nn.Parameter(t) for t in poc]
+    for i in (0, 1, 2, 3, 4, 5, 12, 13, 14, 15):  # freezeBase + freezeDecayUnit
+        ps[i].requires_grad = False
+    assert P.grad_mask_from_requires_grad(ps, "poc") == P.FINE_TUNE_GRAD_MASK
+
+
+def test_indices_to_mask():
+    m, c1, c2 = pk.indices_to_mask(6, (torch.tensor([0, 2]), torch.tensor([0, 0])), torch.tensor([2, 5, 3]), "cpu")
+    assert m.tolist() == [1, 0, 3, 2, 0, 2] and (c1, c2) == (2, 3)
+
+
+def _oracle_trainpy_op(x, y, z, R, i1, i2, *params):
+    """Stand-in for PinnLossTrainPy.apply built on the CPU oracle (tests only): checks the PATCHING."""
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *ps):
+            theta = layout.from_trainpy([p.detach().numpy() for p in ps])
+            n = x.shape[0]
+            m1 = np.zeros(n); m1[i1.numpy()] = 1
+            m2 = np.zeros(n); m2[i2.numpy()] = 1
+            o = cf.loss_and_grad("trainpy", theta, x.detach().numpy(), y.detach().numpy(), z.detach().numpy(),
+                                 R.numpy(), m1, m2)
+            ctx.g = [torch.tensor(a) for a in layout.to_trainpy(o["grad"])]
+            t = lambda v: torch.tensor(v, dtype=torch.float64)
+            outs = (t(o["Ltot"]), t(o["Lpde"]), t(o["Lbc"]), t(o["E"]).reshape(-1, 1))
+            ctx.mark_non_differentiable(*outs[1:])
+            return outs
+
+        @staticmethod
+        def backward(ctx, g, *_):
+            return tuple(g * a for a in ctx.g)
+    return F.apply(*params)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "train.py")), reason="reference not mounted")
+def test_train_py_seam_reproduces_reference_trace(golden_dir, tmp_path):
+    """The reference train.py with lines 41-57 replaced by one call reproduces the unmodified script's trace."""
+    tr = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e40.json")))
+    ns, out = pk.run_train_py(os.path.join(REF, "train.py"), n=4096, epochs=40, workdir=str(tmp_path),
+                              loss_op=_oracle_trainpy_op)
+    torch.set_default_dtype(torch.float32)
+    lines = [ln.strip() for ln in out.strip().split("\n")]
+    assert lines[:3] == tr["trace"][:3]          # identical prints for the first 20 steps
+    assert len(lines) == len(tr["trace"])
+    for a, b in zip(lines, tr["trace"]):          # later steps: same to print precision up to round-off drift
+        fa = [float(v) for v in re.findall(r"[-+]?\d\.\d+e[-+]\d+", a)]
+        fb = [float(v) for v in re.findall(r"[-+]?\d\.\d+e[-+]\d+", b)]
+        assert np.allclose(fa, fb, rtol=2e-2), (a, b)
+    assert os.path.getsize(tmp_path / "model.bin") == tr["model_bin_size"]
+
+
+def test_trainpy_patch_rejects_unknown_source():
+    with pytest.raises(ValueError):
+        pk.trainpy_patched_source("print('hello')\n")
+
+
+def test_patch_nn_ion_signature():
+    calls = []
+
+    class Fake:
+        def LossFunctions(self, x, y, z, R, params, b1, b2):
+            return "orig"
+
+    orig = pk.patch_nn_ion(Fake, loss_fn=lambda m, x, y, z, R, b1, b2: calls.append((x, b2)) or "fused")
+    assert Fake().LossFunctions(1, 2, 3, 4, {"BCcutoff": 17.5}, 5, 6) == "fused" and calls == [(1, 6)]
+    assert orig(Fake(), 1, 2, 3, 4, None, 5, 6) == "orig"
+
+
+DP_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pinn_for_quantum_wavefunction_surfaces_b200 import dp
+from oracle import closed_form as cf
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+gd = os.path.join(sys.argv[1], "tests", "golden")
+theta = np.load(os.path.join(gd, "checkpoints.npz"))["ionHsym"]
+g = np.load(os.path.join(gd, "poc_seed0_n4096.npz"))
+n = g["x"].size
+m1 = np.zeros(n); m1[g["i1"]] = 1
+m2 = np.zeros(n); m2[g["i2"]] = 1
+sl = np.array_split(np.arange(n), world)[rank]
+w = dp.global_weights(len(sl), m1[sl].sum(), m2[sl].sum())
+def local(weights, out):
+    o = cf.loss_and_grad("poc", theta, g["x"][sl], g["y"][sl], g["z"][sl], g["R"][sl], m1[sl], m2[sl], *weights.tolist())
+    out[0], out[1], out[2] = o["Ltot"], o["Lpde"], o["Lbc"]
+    out[3], out[4], out[5], out[6], out[7] = o["sums"]["E"], o["sums"]["res2"], o["sums"]["psi2_1"], o["sums"]["psi2_2"], 0.0
+    out[8:] = torch.from_numpy(o["grad"])
+sums, dth = dp.dp_loss_and_grad(local, w)
+if rank == 0:
+    ref_l, ref_g = g["ionHsym_loss"], g["ionHsym_grad"]
+    assert abs(w[0].item() - 1.0 / n) < 1e-18 and abs(w[1].item() - 1.0 / 2151) < 1e-18
+    assert abs(sums[0].item() - ref_l[0]) / ref_l[0] < 1e-11, (sums[0].item(), ref_l[0])
+    assert abs(sums[2].item() - ref_l[2]) / ref_l[2] < 1e-11
+    assert np.abs(dth.numpy() - ref_g).max() / np.abs(ref_g).max() < 1e-10
+    print("DP_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_two_ranks_gloo(tmp_path):
+    """world_size-2 gloo run of the DP step (oracle as the local compute): sharded result == golden full result."""
+    script = tmp_path / "dp_worker.py"
+    script.write_text(DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
