@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN residual-and-gradient hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P]
+
+A step = one training evaluation (forward + Laplacian + loss + parameter gradients; for N>1 followed
+by the 12 KB gradient all-reduce) of the poc-form ionHsym model on one batch of P synthetic collocation
+points per GPU (default 2^18 = BASELINE config 3; weak scaling: every GPU gets its own P points).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_POINT = 27044.0          # canonical algorithmic FLOPs of one poc training step
+FP32_PEAK_MEASURED = 72.0e12      # tools/microbench/pipes.cu on this pool's B200: 3.60e13 FFMA/s (profiles/r01_microbench_pipes.jsonl)
+FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9
+N_BATCHES = 40                    # rotating input batches: 40 x 4 MiB = 168 MB > 126 MB L2
+
+
+def synth_batch(n, seed, variant="poc"):
+    """x,y,z ~ U(-18,18), R ~ U(0.2,4), clamp at 0.005 from the nuclei (poc/main.py:124-156)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(4, n, generator=g, dtype=torch.float32)
+    x, y, z = (2 * u[0] - 1) * 18, (2 * u[1] - 1) * 18, (2 * u[2] - 1) * 18
+    R = 0.2 + (4.0 - 0.2) * u[3]
+    r1 = torch.sqrt((x - R) ** 2 + y ** 2 + z ** 2)
+    r2 = torch.sqrt((x + R) ** 2 + y ** 2 + z ** 2)
+    x = torch.where((r1 < 0.005) | (r2 < 0.005), torch.full_like(x, 0.005), x)
+    return torch.stack([x, y, z, R]).contiguous()
+
+
+def load_theta():
+    return np.load(os.path.join(ROOT, "tests", "golden", "checkpoints.npz"))["ionHsym"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def cpu_reference_points_per_s(theta, min_seconds, max_points=1 << 16, threads=None):
+    """The reference's own way of computing the step (nested autograd, float64, all host threads):
+    oracle/ref_autograd.py.  Bounded sample: `max_points` points per evaluation, repeated >= min_seconds."""
+    import torch
+    from oracle import ref_autograd as ra
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(1234)
+    x, y, z, R, i1, i2 = ra.sample_box(max_points, "poc", g)
+    th = torch.tensor(theta, dtype=torch.float64)
+    ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)  # warm-up
+    times = []
+    t_all = time.time()
+    while time.time() - t_all < min_seconds or len(times) < 2:
+        t0 = time.time()
+        ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
+        times.append(time.time() - t0)
+    best = min(times)
+    return max_points / best, cores, "%d points x %d evaluations (best of), float64 nested autograd" % (max_points, len(times)), best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    theta = load_theta()
+    import torch
+    from oracle import ref_autograd as ra
+    cores = torch.get_num_threads()
+    ns = 1 << 16
+    g = torch.Generator().manual_seed(1234)
+    x, y, z, R, i1, i2 = ra.sample_box(ns, "poc", g)
+    th = torch.tensor(theta, dtype=torch.float64)
+    for _ in range(max(1, min(args.warmup, 3))):
+        ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
+    steps = max(1, min(args.steps, 40))
+    t0 = time.time()
+    for _ in range(steps):
+        ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
+    dt = (time.time() - t0) / steps
+    v = ns / dt
+    sample = "each step = %d-point sample of the 2^18-point batch; float64 nested autograd (oracle/ref_autograd.py)" % ns
+    print(json.dumps({
+        "impl": "reference", "metric": "collocation points/sec per training step (fwd+lap+bwd)", "value": v,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)",
+                   "sample_points": ns},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 18, help="collocation points per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import pinn_for_quantum_wavefunction_surfaces_b200 as pk
+    from pinn_for_quantum_wavefunction_surfaces_b200 import dp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.points
+    W = max(args.warmup, 3)
+    K = args.steps
+    h = pk.Handle.get(local)
+
+    theta = torch.from_numpy(load_theta().astype(np.float32)).to(dev)
+    host_batches = [synth_batch(n, 1000 * rank + b).pin_memory() for b in range(N_BATCHES)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    out = torch.zeros(dp.N_OUT, dtype=torch.float64, device=dev)
+    # boundary sets are derived in-kernel (r >= 17.5); their global sizes for the 1/count weights come from a
+    # count pass per batch done up front (the sampler knows them in a real run)
+    wts = []
+    for b in dev_batches:
+        r1 = torch.sqrt((b[0] - b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+        r2 = torch.sqrt((b[0] + b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+        wts.append(dp.global_weights(n, int((r1 >= 17.5).sum()), int((r2 >= 17.5).sum()), device=dev))
+
+    def step(i):
+        b = dev_batches[i % N_BATCHES]
+        pk.loss_and_grad_raw(0, b[0], b[1], b[2], b[3], theta, None, wts[i % N_BATCHES], sums=out[:8], dtheta=out[8:])
+        if world > 1:
+            dist.all_reduce(out)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    fence()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = h.launch_count()
+    h.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    t0 = time.time()
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    fence()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = h.profile_collect()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    loss = float(out[0].item())
+
+    # ---- end to end: host buffers through the C ABI (H2D of the batch, kernel, D2H of loss+gradient), every step
+    th64 = load_theta()
+    sums_h = np.zeros(8)
+    dth_h = np.zeros(1521)
+    import ctypes
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    TP = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def e2e_step(i):
+        b = host_batches[i % N_BATCHES]
+        rc = h.L.pinn_loss_fwd_bwd_host(h.h, 0, n, TP(b[0]), TP(b[1]), TP(b[2]), TP(b[3]), 0, None, P(th64), None,
+                                        0xFFFF, 17.5, P(sums_h), P(dth_h), None)
+        h.check(rc, "pinn_loss_fwd_bwd_host")
+        if world > 1:
+            out[:8] = torch.from_numpy(sums_h).to(dev)
+            out[8:] = torch.from_numpy(dth_h).to(dev)
+            dist.all_reduce(out)
+
+    Ke = max(3, min(K, 50))
+    for i in range(3):
+        e2e_step(i)
+    fence()
+    te0 = time.time()
+    for i in range(Ke):
+        e2e_step(3 + i)
+    fence()
+    te = (time.time() - te0) / Ke
+    tte = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tte, op=dist.ReduceOp.MAX)
+    te = float(tte.item())
+
+    if rank == 0:
+        total_points = float(n) * world
+        value = total_points * K / (ms * 1e-3)
+        kern_avg_ms = kern_ms / max(kern_n, 1)
+        achieved = FLOP_PER_POINT * n / (kern_avg_ms * 1e-3)
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "collocation points/sec per training step (fwd+lap+bwd)",
+            "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)",
+                       "points_per_gpu": n, "global_points": int(total_points), "weights": "models/ionHsym.pt (tests/golden/checkpoints.npz)",
+                       "inputs": "%d rotating batches resident in HBM, %.0f MB > 126 MB L2" % (N_BATCHES, N_BATCHES * n * 16 / 1e6),
+                       "parallelism": "dp%d point sharding + 1 all-reduce of 1529 f64" % world if world > 1 else "single GPU"},
+            "roofline": {"bound": "fp32_ffma", "achieved": achieved / 1e12, "peak": FP32_PEAK_MEASURED / 1e12,
+                         "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_MEASURED,
+                         "frac_of_nominal_74.4": achieved / FP32_PEAK_NOMINAL,
+                         "peak_source": "measured FFMA rate on this pool's B200 (tools/microbench/pipes.cu); MEASURED_PEAKS.json has no FP32 entry",
+                         "flop_per_point": FLOP_PER_POINT, "kernel": "pinn_step_kernel<2,G,true>",
+                         "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic},
+            "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
+                    "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke,
+                    "api": "pinn_loss_fwd_bwd_host (pinned float32 host batches)"},
+            "gpu_launches": int(launches), "clocks": clocks, "loss": loss,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,12 +26,16 @@
 
 namespace pinn {
 
-constexpr int LDH = 72;  // row stride (floats) of the per-point stash of an MLP warp: 4 channels x 16, padded so
-                         // that both mma fragment loads (bank = 8*t + g) are conflict free
-constexpr int LDE = 40;  // row stride of the E-net warp stash (32 used)
-constexpr int EVAL_STASH = 2 * 32 * LDH;  // floats: Hs + Gs
-constexpr int ENET_STASH = 2 * 32 * LDE;  // floats: E1s + Vs
+// Per-point stash rows live in shared memory, one row per lane (= point): 64 floats for an MLP warp
+// (4 Taylor channels x 16), 32 for the E-net warp.  Rows are NOT padded; instead the column index is
+// XOR-swizzled with 8*(row&3), which makes the mma fragment loads (rows t / t+4, columns g / g+8)
+// conflict free and keeps float4 groups intact.
+constexpr int ROWH = 64;
+constexpr int ROWE = 32;
+constexpr int EVAL_STASH = 2 * 32 * ROWH;  // floats: Hs + Gs
+constexpr int ENET_STASH = 2 * 32 * ROWE;  // floats: E1s + Vs
 
+__device__ __forceinline__ int swz(int row) { return (row & 3) << 3; }
 
 // ---------------------------------------------------------------------------------------------
 // small PTX helpers
@@ -68,27 +72,36 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4
   mma_tf32(c, ah, bh0, bh1);
 }
 
-// Transposing butterfly: on entry every lane holds 32 values v[i] (its point's contribution to
-// output i); on exit the return value of lane L is sum over lanes of v[L].  31 SHFL + 31 FADD.
-template <int N>
-__device__ __forceinline__ void bfly_stage(float (&v)[32], int lane) {
-  constexpr int H = N / 2;
-  const bool up = (lane & H) != 0;
-#pragma unroll
-  for (int i = 0; i < H; i++) {
-    const float lo = v[i], hi = v[i + H];
-    const float send = up ? lo : hi;
-    const float keep = up ? hi : lo;
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+// Column sum over the 32 rows (points) of a swizzled stash: lane sums column `col`.
+template <int ROW>
+__device__ __forceinline__ float colsum(const float* __restrict__ base, int col) {
+  const float* p0 = base + col;
+  const float* p1 = base + ROW + (col ^ 8);
+  const float* p2 = base + 2 * ROW + (col ^ 16);
+  const float* p3 = base + 3 * ROW + (col ^ 24);
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 2
+  for (int p = 0; p < 32; p += 4) {
+    s0 += p0[p * ROW]; s1 += p1[p * ROW]; s2 += p2[p * ROW]; s3 += p3[p * ROW];
   }
+  return (s0 + s1) + (s2 + s3);
 }
-__device__ __forceinline__ float bfly32(float (&v)[32], int lane) {
-  bfly_stage<32>(v, lane);
-  bfly_stage<16>(v, lane);
-  bfly_stage<8>(v, lane);
-  bfly_stage<4>(v, lane);
-  bfly_stage<2>(v, lane);
-  return v[0];
+// Weighted column sums: returns sum_p base[p][col] and sum_p wgt_p * base[p][col] (wgt = per-lane value of row p)
+template <int ROW>
+__device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col, float wgt, float& plain, float& weighted) {
+  float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
+#pragma unroll 2
+  for (int p = 0; p < 32; p += 4) {
+    const float v0 = base[(p + 0) * ROW + col], v1 = base[(p + 1) * ROW + (col ^ 8)];
+    const float v2 = base[(p + 2) * ROW + (col ^ 16)], v3 = base[(p + 3) * ROW + (col ^ 24)];
+    s0 += v0; s1 += v1; s0 += v2; s1 += v3;
+    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 0), v0, t0);
+    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 1), v1, t1);
+    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 2), v2, t0);
+    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 3), v3, t1);
+  }
+  plain = s0 + s1;
+  weighted = t0 + t1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -135,24 +148,23 @@ __device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) {
   return g;
 }
 
+#define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
+#define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))
+
 // ---------------------------------------------------------------------------------------------
 // base MLP, one evaluation at (a,b): 4-channel Taylor forward (value, d/da, d/db, D)
-//   Hs row (this lane's point): h_c[k]  at [c*16+k]   (kept for the dW2 contraction and the reverse sweep)
-//   Gs row:                     t_j, va_j, vb_j, vD_j at [c*16+j]  (overwritten by the adjoints later)
+//   Hs row (this lane's point): h_c[k]  at column c*16+k   (kept for the dW2 contraction and the reverse sweep)
+//   Gs row:                     t_j, va_j, vb_j, vD_j at column c*16+j  (overwritten by the adjoints later)
 // ---------------------------------------------------------------------------------------------
 template <bool STASH>
 __device__ __forceinline__ void mlp_forward(const Wts& w, float a, float b, float al1, float al2, float al11,
                                             float al12, float al22, float* __restrict__ Hrow,
-                                            float* __restrict__ Grow, float& Nv, float& Dv) {
+                                            float* __restrict__ Grow, int sx, float& Nv, float& Dv) {
   float h[4][NH];
 #pragma unroll
   for (int k4 = 0; k4 < NH; k4 += 4) {
-    const float4 w0v = *reinterpret_cast<const float4*>(&w.w0[k4]);
-    const float4 w1v = *reinterpret_cast<const float4*>(&w.w1[k4]);
-    const float4 b1v = *reinterpret_cast<const float4*>(&w.b1[k4]);
-    const float4 q00 = *reinterpret_cast<const float4*>(&w.ww00[k4]);
-    const float4 q01 = *reinterpret_cast<const float4*>(&w.ww01[k4]);
-    const float4 q11 = *reinterpret_cast<const float4*>(&w.ww11[k4]);
+    const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]), b1v = LD4(&w.b1[k4]);
+    const float4 q00 = LD4(&w.ww00[k4]), q01 = LD4(&w.ww01[k4]), q11 = LD4(&w.ww11[k4]);
     const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
     const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
     const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
@@ -177,22 +189,21 @@ __device__ __forceinline__ void mlp_forward(const Wts& w, float a, float b, floa
     for (int c = 0; c < 4; c++)
 #pragma unroll
       for (int k4 = 0; k4 < NH; k4 += 4)
-        *reinterpret_cast<float4*>(&Hrow[c * NH + k4]) = make_float4(h[c][k4], h[c][k4 + 1], h[c][k4 + 2], h[c][k4 + 3]);
+        ST4(&Hrow[(c * NH + k4) ^ sx], h[c][k4], h[c][k4 + 1], h[c][k4 + 2], h[c][k4 + 3]);
   }
   float accN = 0.0f, accD = 0.0f;
-#pragma unroll
+#pragma unroll 1
   for (int j4 = 0; j4 < NH; j4 += 4) {
     float tt[4], va[4], vb[4], vD[4];
-    const float4 b2v = *reinterpret_cast<const float4*>(&w.b2[j4]);
-    const float4 wov = *reinterpret_cast<const float4*>(&w.wo[j4]);
+    const float4 b2v = LD4(&w.b2[j4]), wov = LD4(&w.wo[j4]);
     const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int j = j4 + i;
+      const float* wrow = &w.W2[(j4 + i) * NH];
       float v0 = b2a[i], v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
 #pragma unroll
       for (int k4 = 0; k4 < NH; k4 += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&w.W2[j * NH + k4]);
+        const float4 wv = LD4(&wrow[k4]);
         const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
@@ -212,10 +223,10 @@ __device__ __forceinline__ void mlp_forward(const Wts& w, float a, float b, floa
       tt[i] = t; va[i] = v1; vb[i] = v2; vD[i] = v3;
     }
     if (STASH) {
-      *reinterpret_cast<float4*>(&Grow[0 * NH + j4]) = make_float4(tt[0], tt[1], tt[2], tt[3]);
-      *reinterpret_cast<float4*>(&Grow[1 * NH + j4]) = make_float4(va[0], va[1], va[2], va[3]);
-      *reinterpret_cast<float4*>(&Grow[2 * NH + j4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
-      *reinterpret_cast<float4*>(&Grow[3 * NH + j4]) = make_float4(vD[0], vD[1], vD[2], vD[3]);
+      ST4(&Grow[(0 * NH + j4) ^ sx], tt[0], tt[1], tt[2], tt[3]);
+      ST4(&Grow[(1 * NH + j4) ^ sx], va[0], va[1], va[2], va[3]);
+      ST4(&Grow[(2 * NH + j4) ^ sx], vb[0], vb[1], vb[2], vb[3]);
+      ST4(&Grow[(3 * NH + j4) ^ sx], vD[0], vD[1], vD[2], vD[3]);
     }
   }
   Nv = accN;
@@ -225,27 +236,27 @@ __device__ __forceinline__ void mlp_forward(const Wts& w, float a, float b, floa
 // persistent per-lane accumulators of an MLP warp
 struct MlpAcc {
   float cW2[2][4];   // mma C fragments of dW2 (16x16): n-tile 0/1
-  float s0, s1;      // butterfly chunks: {dwo[16], db2[16]}, {dw0[16], dw1[16]}
-  double s2;         // {db1[16], loss sums (role 0)}: double because the loss sums ride here
+  float s0;          // lane<16: db2[lane]        lane>=16: dwo[lane-16]
+  float s1;          // lane<16: dW1[lane][0]     lane>=16: dW1[lane-16][1]
+  float s2;          // lane<16: db1[lane]        lane>=16: extra[lane-16] (loss sums, role 0)
 };
 
 // Reverse sweep of one MLP evaluation for the seeds lamN = dL/dNv, lamD = dL/dDv
-// (oracle/closed_form.py:mlp_bwd).  `extra` are 16 more per-point values reduced with db1.
+// (oracle/closed_form.py:mlp_bwd).  `extra` are 8 more per-point values summed over the tile.
 __device__ __forceinline__ void mlp_backward(const Wts& w, float a, float b, float al1, float al2, float al11,
                                              float al12, float al22, float lamN, float lamD,
                                              float* __restrict__ Hs, float* __restrict__ Gs, int lane,
-                                             const float (&extra)[16], MlpAcc& acc) {
-  float* Hrow = Hs + lane * LDH;
-  float* Grow = Gs + lane * LDH;
+                                             const float (&extra)[8], MlpAcc& acc) {
+  const int sx = swz(lane);
+  float* Hrow = Hs + lane * ROWH;
+  float* Grow = Gs + lane * ROWH;
   float vbar[4][NH];
-  float ch0[32];  // dwo | db2
+  float dwo[NH];
 #pragma unroll
   for (int j4 = 0; j4 < NH; j4 += 4) {
-    const float4 tv = *reinterpret_cast<const float4*>(&Grow[0 * NH + j4]);
-    const float4 av = *reinterpret_cast<const float4*>(&Grow[1 * NH + j4]);
-    const float4 bv = *reinterpret_cast<const float4*>(&Grow[2 * NH + j4]);
-    const float4 dv = *reinterpret_cast<const float4*>(&Grow[3 * NH + j4]);
-    const float4 wov = *reinterpret_cast<const float4*>(&w.wo[j4]);
+    const float4 tv = LD4(&Grow[(0 * NH + j4) ^ sx]), av = LD4(&Grow[(1 * NH + j4) ^ sx]);
+    const float4 bv = LD4(&Grow[(2 * NH + j4) ^ sx]), dv = LD4(&Grow[(3 * NH + j4) ^ sx]);
+    const float4 wov = LD4(&w.wo[j4]);
     const float ta[4] = {tv.x, tv.y, tv.z, tv.w}, vaa[4] = {av.x, av.y, av.z, av.w};
     const float vba[4] = {bv.x, bv.y, bv.z, bv.w}, vDa[4] = {dv.x, dv.y, dv.z, dv.w};
     const float woa[4] = {wov.x, wov.y, wov.z, wov.w};
@@ -259,72 +270,71 @@ __device__ __forceinline__ void mlp_backward(const Wts& w, float a, float b, flo
       const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
       const float gD = fmaf(tp, v3, tpp * Q);
       const float tbar = lamN * woa[i], gDbar = lamD * woa[i];
-      ch0[j] = fmaf(lamN, t, lamD * gD);
+      dwo[j] = fmaf(lamN, t, lamD * gD);
       const float c2 = gDbar * tpp;
       vbar[3][j] = gDbar * tp;
       vbar[1][j] = c2 * fmaf(2.0f * al11, v1, al12 * v2);
       vbar[2][j] = c2 * fmaf(al12, v1, 2.0f * al22 * v2);
       vbar[0][j] = fmaf(tbar, tp, gDbar * fmaf(tpp, v3, tppp * Q));
-      ch0[16 + j] = vbar[0][j];
     }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      ST4(&Grow[(c * NH + j4) ^ sx], vbar[c][j4], vbar[c][j4 + 1], vbar[c][j4 + 2], vbar[c][j4 + 3]);
   }
-#pragma unroll
-  for (int c = 0; c < 4; c++)
-#pragma unroll
-    for (int j4 = 0; j4 < NH; j4 += 4)
-      *reinterpret_cast<float4*>(&Grow[c * NH + j4]) =
-          make_float4(vbar[c][j4], vbar[c][j4 + 1], vbar[c][j4 + 2], vbar[c][j4 + 3]);
   __syncwarp();
 
   // ---- dW2[j][k] += sum_{p,c} G[p][c][j] * H[p][c][k] on the tensor cores (3xTF32) ----
   {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
+    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+#pragma unroll 1
     for (int c = 0; c < 4; c++) {
 #pragma unroll
       for (int po = 0; po < 4; po++) {
-        const float* Ga = Gs + (po * 8 + t) * LDH + c * NH;
-        const float* Gb = Ga + 4 * LDH;
-        const float* Ha = Hs + (po * 8 + t) * LDH + c * NH;
-        const float* Hb = Ha + 4 * LDH;
+        const float* Ga = Gs + (po * 8 + t) * ROWH;
+        const float* Gb = Ga + 4 * ROWH;
+        const float* Ha = Hs + (po * 8 + t) * ROWH;
+        const float* Hb = Ha + 4 * ROWH;
+        const int ca = (c * NH + g) ^ tx, cb = (c * NH + g + 8) ^ tx;
         uint32_t ah[4], al[4];
-        split_tf32(Ga[g], ah[0], al[0]);
-        split_tf32(Ga[g + 8], ah[1], al[1]);
-        split_tf32(Gb[g], ah[2], al[2]);
-        split_tf32(Gb[g + 8], ah[3], al[3]);
-#pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(Ha[nt * 8 + g], bh0, bl0);
-          split_tf32(Hb[nt * 8 + g], bh1, bl1);
-          mma_3xtf32(acc.cW2[nt], ah, al, bh0, bh1, bl0, bl1);
-        }
+        split_tf32(Ga[ca], ah[0], al[0]);
+        split_tf32(Ga[cb], ah[1], al[1]);
+        split_tf32(Gb[ca], ah[2], al[2]);
+        split_tf32(Gb[cb], ah[3], al[3]);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Ha[ca], bh0, bl0);
+        split_tf32(Hb[ca], bh1, bl1);
+        mma_3xtf32(acc.cW2[0], ah, al, bh0, bh1, bl0, bl1);
+        split_tf32(Ha[cb], bh0, bl0);
+        split_tf32(Hb[cb], bh1, bl1);
+        mma_3xtf32(acc.cW2[1], ah, al, bh0, bh1, bl0, bl1);
       }
     }
   }
-  acc.s0 += bfly32(ch0, lane);
-
-  // ---- hbar = W2^T vbar, then layer-1 reverse sweep neuron by neuron ----
-  float ch1[32], ch2[32];
+  __syncwarp();  // all fragment loads done: channel 1..3 regions of the stash rows may be reused
+  // ---- db2 (= column sums of vbar channel 0) and dwo ----
 #pragma unroll
+  for (int j4 = 0; j4 < NH; j4 += 4) ST4(&Grow[(NH + j4) ^ sx], dwo[j4], dwo[j4 + 1], dwo[j4 + 2], dwo[j4 + 3]);
+  __syncwarp();
+  acc.s0 += colsum<ROWH>(Gs, lane);
+
+  // ---- hbar = W2^T vbar, then layer-1 reverse sweep, 4 neurons per iteration ----
+#pragma unroll 1
   for (int k4 = 0; k4 < NH; k4 += 4) {
-    const float4 sv = *reinterpret_cast<const float4*>(&Hrow[k4]);  // h channel 0 = s_k
-    const float4 w0v = *reinterpret_cast<const float4*>(&w.w0[k4]);
-    const float4 w1v = *reinterpret_cast<const float4*>(&w.w1[k4]);
-    const float4 q00 = *reinterpret_cast<const float4*>(&w.ww00[k4]);
-    const float4 q01 = *reinterpret_cast<const float4*>(&w.ww01[k4]);
-    const float4 q11 = *reinterpret_cast<const float4*>(&w.ww11[k4]);
+    const float4 sv = LD4(&Hrow[k4 ^ sx]);  // h channel 0 = s_k
+    const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]);
+    const float4 q00 = LD4(&w.ww00[k4]), q01 = LD4(&w.ww01[k4]), q11 = LD4(&w.ww11[k4]);
     const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
     const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
     const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
     const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+    float o0[4], o1[4], ob[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int k = k4 + i;
+      const float* wrow = &w.W2T[(k4 + i) * NH];
       float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
       for (int j4 = 0; j4 < NH; j4 += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&w.W2T[k * NH + j4]);
+        const float4 wv = LD4(&wrow[j4]);
         const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
@@ -341,15 +351,33 @@ __device__ __forceinline__ void mlp_backward(const Wts& w, float a, float b, flo
       const float d1 = fmaf(al1, w0, al2 * w1);
       const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
       const float ubar = fmaf(h0, sp, fmaf(fmaf(h1, w0, fmaf(h2, w1, h3 * d1)), spp, h3 * q * sppp));
-      ch1[k] = fmaf(h1, sp, fmaf(h3, fmaf(sp, al1, spp * fmaf(2.0f * al11, w0, al12 * w1)), ubar * a));
-      ch1[16 + k] = fmaf(h2, sp, fmaf(h3, fmaf(sp, al2, spp * fmaf(al12, w0, 2.0f * al22 * w1)), ubar * b));
-      ch2[k] = ubar;
+      o0[i] = fmaf(h1, sp, fmaf(h3, fmaf(sp, al1, spp * fmaf(2.0f * al11, w0, al12 * w1)), ubar * a));
+      o1[i] = fmaf(h2, sp, fmaf(h3, fmaf(sp, al2, spp * fmaf(al12, w0, 2.0f * al22 * w1)), ubar * b));
+      ob[i] = ubar;
     }
+    ST4(&Hrow[(1 * NH + k4) ^ sx], o0[0], o0[1], o0[2], o0[3]);
+    ST4(&Hrow[(2 * NH + k4) ^ sx], o1[0], o1[1], o1[2], o1[3]);
+    ST4(&Hrow[(3 * NH + k4) ^ sx], ob[0], ob[1], ob[2], ob[3]);
   }
-#pragma unroll
-  for (int i = 0; i < 16; i++) ch2[16 + i] = extra[i];
-  acc.s1 += bfly32(ch1, lane);
-  acc.s2 += (double)bfly32(ch2, lane);
+  ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
+  ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
+  __syncwarp();
+  acc.s1 += colsum<ROWH>(Hs, NH + lane);                          // columns 16..47: dw0 | dw1
+  acc.s2 += colsum<ROWH>(Hs, lane < 16 ? 3 * NH + lane : lane - 16);  // columns 48..63: db1 ; 0..15: extras
+  __syncwarp();
+}
+
+// loss sums only (fine-tune mode: no base-MLP reverse sweep); role 0
+__device__ __forceinline__ void mlp_extras_only(float* __restrict__ Hs, int lane, const float (&extra)[8], MlpAcc& acc) {
+  const int sx = swz(lane);
+  float* Hrow = Hs + lane * ROWH;
+  __syncwarp();
+  ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
+  ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
+  __syncwarp();
+  const float v = colsum<ROWH>(Hs, lane & 7);
+  if (lane >= 16 && lane < 24) acc.s2 += v;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,33 +385,30 @@ __device__ __forceinline__ void mlp_backward(const Wts& w, float a, float b, flo
 // ---------------------------------------------------------------------------------------------
 template <bool STASH>
 __device__ __forceinline__ float enet_forward(const Wts& w, float R, float* __restrict__ E1row,
-                                              float* __restrict__ Vrow) {
+                                              float* __restrict__ Vrow, int sx) {
   float e1[NE];
 #pragma unroll
   for (int k4 = 0; k4 < NE; k4 += 4) {
-    const float4 wv = *reinterpret_cast<const float4*>(&w.WE1[k4]);
-    const float4 bv = *reinterpret_cast<const float4*>(&w.bE1[k4]);
+    const float4 wv = LD4(&w.WE1[k4]), bv = LD4(&w.bE1[k4]);
     e1[k4 + 0] = sigm(fmaf(R, wv.x, bv.x));
     e1[k4 + 1] = sigm(fmaf(R, wv.y, bv.y));
     e1[k4 + 2] = sigm(fmaf(R, wv.z, bv.z));
     e1[k4 + 3] = sigm(fmaf(R, wv.w, bv.w));
-    if (STASH) *reinterpret_cast<float4*>(&E1row[k4]) = make_float4(e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
+    if (STASH) ST4(&E1row[k4 ^ sx], e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
   }
   float E = w.bE;
-#pragma unroll
+#pragma unroll 1
   for (int j4 = 0; j4 < NE; j4 += 4) {
-    const float4 b2v = *reinterpret_cast<const float4*>(&w.bE2[j4]);
-    const float4 wEv = *reinterpret_cast<const float4*>(&w.wE[j4]);
+    const float4 b2v = LD4(&w.bE2[j4]), wEv = LD4(&w.wE[j4]);
     const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
     float e2[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int j = j4 + i;
+      const float* wrow = &w.WE2[(j4 + i) * NE];
       float v0 = b2a[i], v1 = 0.0f;  // two partial sums for ILP
 #pragma unroll
       for (int k4 = 0; k4 < NE; k4 += 8) {
-        const float4 wa = *reinterpret_cast<const float4*>(&w.WE2[j * NE + k4]);
-        const float4 wb = *reinterpret_cast<const float4*>(&w.WE2[j * NE + k4 + 4]);
+        const float4 wa = LD4(&wrow[k4]), wb = LD4(&wrow[k4 + 4]);
         v0 = fmaf(wa.x, e1[k4 + 0], v0); v0 = fmaf(wa.y, e1[k4 + 1], v0);
         v0 = fmaf(wa.z, e1[k4 + 2], v0); v0 = fmaf(wa.w, e1[k4 + 3], v0);
         v1 = fmaf(wb.x, e1[k4 + 4], v1); v1 = fmaf(wb.y, e1[k4 + 5], v1);
@@ -392,7 +417,7 @@ __device__ __forceinline__ float enet_forward(const Wts& w, float R, float* __re
       e2[i] = sigm(v0 + v1);
       E = fmaf(wEa[i], e2[i], E);
     }
-    if (STASH) *reinterpret_cast<float4*>(&Vrow[j4]) = make_float4(e2[0], e2[1], e2[2], e2[3]);
+    if (STASH) ST4(&Vrow[j4 ^ sx], e2[0], e2[1], e2[2], e2[3]);
   }
   return E;
 }
@@ -406,95 +431,86 @@ __device__ __forceinline__ float gate_forward(const Wts& w, float R) {
 
 struct EnetAcc {
   float cWE2[2][4][4];         // mma C fragments of dWE2 (32x32): [m-tile][n-tile]
-  float s0, s1, s2, s3, s4;    // butterfly chunks: dwE, dbE2, dWE1, dbE1, {dWgL,dbgL,dwg,dbg,dbE}
+  float s0, s1, s2, s3, s4;    // per lane: dwE[lane], dbE2[lane], dWE1[lane], dbE1[lane], {dWgL,dbgL,dwg,dbg,dbE}[lane]
 };
 
 // Reverse sweep of the E-net and gate for the seeds Ebar = dL/dE, gbar = dL/dgate.
 __device__ __forceinline__ void enet_backward(const Wts& w, float R, float Ebar, float gbar, bool gate_grads,
                                               float* __restrict__ E1s, float* __restrict__ Vs, int lane,
                                               EnetAcc& acc) {
-  float* E1row = E1s + lane * LDE;
-  float* Vrow = Vs + lane * LDE;
-  float vbar[NE];
+  const int sx = swz(lane);
+  float* E1row = E1s + lane * ROWE;
+  float* Vrow = Vs + lane * ROWE;
+  __syncwarp();
+  // ---- dwE[j] = sum_p Ebar_p e2[p][j] (Vs still holds e2) ----
   {
-    float ch[32];
+    float plain, weighted;
+    colsum_w<ROWE>(Vs, lane, Ebar, plain, weighted);
+    acc.s0 += weighted;
+  }
+  __syncwarp();
+  float vbar[NE];
 #pragma unroll
-    for (int j4 = 0; j4 < NE; j4 += 4) {
-      const float4 ev = *reinterpret_cast<const float4*>(&Vrow[j4]);
-      const float4 wEv = *reinterpret_cast<const float4*>(&w.wE[j4]);
-      const float ea[4] = {ev.x, ev.y, ev.z, ev.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
+  for (int j4 = 0; j4 < NE; j4 += 4) {
+    const float4 ev = LD4(&Vrow[j4 ^ sx]), wEv = LD4(&w.wE[j4]);
+    const float ea[4] = {ev.x, ev.y, ev.z, ev.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        ch[j4 + i] = Ebar * ea[i];
-        vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
-      }
-      *reinterpret_cast<float4*>(&Vrow[j4]) = make_float4(vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
-    }
-    acc.s0 += bfly32(ch, lane);
+    for (int i = 0; i < 4; i++) vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
+    ST4(&Vrow[j4 ^ sx], vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
   }
   __syncwarp();
   // ---- dWE2[j][k] += sum_p V[p][j] * E1[p][k] on the tensor cores (3xTF32) ----
   {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
+    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+#pragma unroll 1
     for (int ks = 0; ks < 4; ks++) {
-      const float* Va = Vs + (ks * 8 + t) * LDE;
-      const float* Vb = Va + 4 * LDE;
-      const float* Ea = E1s + (ks * 8 + t) * LDE;
-      const float* Eb = Ea + 4 * LDE;
+      const float* Va = Vs + (ks * 8 + t) * ROWE;
+      const float* Vb = Va + 4 * ROWE;
+      const float* Ea = E1s + (ks * 8 + t) * ROWE;
+      const float* Eb = Ea + 4 * ROWE;
       uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
-        split_tf32(Va[mt * 16 + g], ah[mt][0], al[mt][0]);
-        split_tf32(Va[mt * 16 + g + 8], ah[mt][1], al[mt][1]);
-        split_tf32(Vb[mt * 16 + g], ah[mt][2], al[mt][2]);
-        split_tf32(Vb[mt * 16 + g + 8], ah[mt][3], al[mt][3]);
+        split_tf32(Va[(mt * 16 + g) ^ tx], ah[mt][0], al[mt][0]);
+        split_tf32(Va[(mt * 16 + g + 8) ^ tx], ah[mt][1], al[mt][1]);
+        split_tf32(Vb[(mt * 16 + g) ^ tx], ah[mt][2], al[mt][2]);
+        split_tf32(Vb[(mt * 16 + g + 8) ^ tx], ah[mt][3], al[mt][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
         uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(Ea[nt * 8 + g], bh0, bl0);
-        split_tf32(Eb[nt * 8 + g], bh1, bl1);
+        split_tf32(Ea[(nt * 8 + g) ^ tx], bh0, bl0);
+        split_tf32(Eb[(nt * 8 + g) ^ tx], bh1, bl1);
         mma_3xtf32(acc.cWE2[0][nt], ah[0], al[0], bh0, bh1, bl0, bl1);
         mma_3xtf32(acc.cWE2[1][nt], ah[1], al[1], bh0, bh1, bl0, bl1);
       }
     }
   }
-  {
-    float ch[32];
+  acc.s1 += colsum<ROWE>(Vs, lane);  // dbE2
+  __syncwarp();                      // Vs rows may now be overwritten
+  // ---- e1bar = WE2^T vbar, layer-1 reverse sweep; ubar_k -> Vs row ----
+#pragma unroll 1
+  for (int k4 = 0; k4 < NE; k4 += 4) {
+    const float4 ev = LD4(&E1row[k4 ^ sx]);
+    const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
+    float ub[4];
 #pragma unroll
-    for (int i = 0; i < 32; i++) ch[i] = vbar[i];
-    acc.s1 += bfly32(ch, lane);
-  }
-  // ---- e1bar = WE2^T vbar, layer-1 reverse sweep ----
-  {
-    float chW[32], chB[32];
+    for (int i = 0; i < 4; i++) {
+      const float* wrow = &w.WE2T[(k4 + i) * NE];
+      float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-    for (int k4 = 0; k4 < NE; k4 += 4) {
-      const float4 ev = *reinterpret_cast<const float4*>(&E1row[k4]);
-      const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int k = k4 + i;
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-        for (int j4 = 0; j4 < NE; j4 += 8) {
-          const float4 wa = *reinterpret_cast<const float4*>(&w.WE2T[k * NE + j4]);
-          const float4 wb = *reinterpret_cast<const float4*>(&w.WE2T[k * NE + j4 + 4]);
-          s0 = fmaf(wa.x, vbar[j4 + 0], s0); s0 = fmaf(wa.y, vbar[j4 + 1], s0);
-          s0 = fmaf(wa.z, vbar[j4 + 2], s0); s0 = fmaf(wa.w, vbar[j4 + 3], s0);
-          s1 = fmaf(wb.x, vbar[j4 + 4], s1); s1 = fmaf(wb.y, vbar[j4 + 5], s1);
-          s1 = fmaf(wb.z, vbar[j4 + 6], s1); s1 = fmaf(wb.w, vbar[j4 + 7], s1);
-        }
-        const float ub = (s0 + s1) * fmaf(-ea[i], ea[i], ea[i]);
-        chW[k] = ub * R;
-        chB[k] = ub;
+      for (int j4 = 0; j4 < NE; j4 += 8) {
+        const float4 wa = LD4(&wrow[j4]), wb = LD4(&wrow[j4 + 4]);
+        s0 = fmaf(wa.x, vbar[j4 + 0], s0); s0 = fmaf(wa.y, vbar[j4 + 1], s0);
+        s0 = fmaf(wa.z, vbar[j4 + 2], s0); s0 = fmaf(wa.w, vbar[j4 + 3], s0);
+        s1 = fmaf(wb.x, vbar[j4 + 4], s1); s1 = fmaf(wb.y, vbar[j4 + 5], s1);
+        s1 = fmaf(wb.z, vbar[j4 + 6], s1); s1 = fmaf(wb.w, vbar[j4 + 7], s1);
       }
+      ub[i] = (s0 + s1) * fmaf(-ea[i], ea[i], ea[i]);
     }
-    acc.s2 += bfly32(chW, lane);
-    acc.s3 += bfly32(chB, lane);
+    ST4(&Vrow[k4 ^ sx], ub[0], ub[1], ub[2], ub[3]);
   }
-  // ---- gate reverse sweep + dbE ----
+  // ---- gate reverse sweep + dbE -> E1s row (free now) ----
   {
     float ch[32];
 #pragma unroll
@@ -507,8 +523,18 @@ __device__ __forceinline__ void enet_backward(const Wts& w, float R, float Ebar,
     }
     ch[30] = gate_grads ? gbar : 0.0f;
     ch[31] = Ebar;
-    acc.s4 += bfly32(ch, lane);
+#pragma unroll
+    for (int c4 = 0; c4 < 32; c4 += 4) ST4(&E1row[c4 ^ sx], ch[c4], ch[c4 + 1], ch[c4 + 2], ch[c4 + 3]);
   }
+  __syncwarp();
+  {
+    float plain, weighted;
+    colsum_w<ROWE>(Vs, lane, R, plain, weighted);
+    acc.s2 += weighted;  // dWE1[k] = sum_p ubar_k R_p
+    acc.s3 += plain;     // dbE1
+  }
+  acc.s4 += colsum<ROWE>(E1s, lane);
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,6 +560,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = warp / WPG, role = warp % WPG;  // role < NEV: MLP evaluation; role == NEV: E-net + gate
   const bool is_mlp = role < NEV;
+  const int sx = swz(lane);
 
   // ---- stage the weight image once per CTA: TMA bulk copy global -> shared, completion on an mbarrier ----
   if (tid == 0) {
@@ -565,7 +592,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
 
   float* gstash = stash + grp * group_stash_floats<NEV>();
   float* Hs = gstash + (is_mlp ? role * EVAL_STASH : NEV * EVAL_STASH);
-  float* Gs = Hs + (is_mlp ? 32 * LDH : 32 * LDE);  // for the E-net warp: Hs = E1s, Gs = Vs
+  float* Gs = Hs + (is_mlp ? 32 * ROWH : 32 * ROWE);  // for the E-net warp: Hs = E1s, Gs = Vs
   float2* gbox = mbox + grp * (2 * 3 * 32);
 
   double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
@@ -579,7 +606,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
   for (int i = 0; i < 2; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) macc.cW2[i][j] = 0.0f;
-  macc.s0 = macc.s1 = 0.0f; macc.s2 = 0.0;
+  macc.s0 = macc.s1 = macc.s2 = 0.0f;
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -607,10 +634,10 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
 
     if (is_mlp) {
       float Nv, Dv;
-      mlp_forward<TRAIN>(w, a, b, al1, al2, al11, al12, al22, Hs + lane * LDH, Gs + lane * LDH, Nv, Dv);
+      mlp_forward<TRAIN>(w, a, b, al1, al2, al11, al12, al22, Hs + lane * ROWH, Gs + lane * ROWH, sx, Nv, Dv);
       box[role * 32 + lane] = make_float2(Nv, Dv);
     } else {
-      const float E = enet_forward<TRAIN>(w, g.R, Hs + lane * LDE, Gs + lane * LDE);
+      const float E = enet_forward<TRAIN>(w, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx);
       const float gt = gate_forward(w, g.R);
       box[2 * 32 + lane] = make_float2(E, gt);
     }
@@ -662,9 +689,9 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
     if (is_mlp) {
       const float lamN = fmaf(rbar, gate * fmaf(cV, q, cE * E), pbar * gate);
       const float lamD = rbar * cL * gate;
-      float extra[16];
+      float extra[8];
 #pragma unroll
-      for (int i = 0; i < 16; i++) extra[i] = 0.0f;
+      for (int i = 0; i < 8; i++) extra[i] = 0.0f;
       if (role == 0) {
         extra[0] = res * res * vw;
         extra[1] = psi * psi * m1f * vw;
@@ -677,10 +704,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
       if (p.base_grads) {
         mlp_backward(w, a, b, al1, al2, al11, al12, al22, sN * lamN, sN * lamD, Hs, Gs, lane, extra, macc);
       } else if (role == 0) {
-        float ch[32];
-#pragma unroll
-        for (int i = 0; i < 16; i++) { ch[i] = 0.0f; ch[16 + i] = extra[i]; }
-        macc.s2 += (double)bfly32(ch, lane);
+        mlp_extras_only(Hs, lane, extra, macc);
       }
     } else {
       if (valid && p.E_out) p.E_out[pidx] = E;
@@ -709,7 +733,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
           red[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] += macc.cW2[nt][2];
           red[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] += macc.cW2[nt][3];
         }
-        red[lane < 16 ? O_WO + lane : O_B2 + lane - 16] += macc.s0;
+        red[lane < 16 ? O_B2 + lane : O_WO + lane - 16] += macc.s0;
         red[lane < 16 ? O_W1 + 2 * lane : O_W1 + 2 * (lane - 16) + 1] += macc.s1;
         if (lane < 16) red[O_B1 + lane] += macc.s2;
         else if (role == 0) {
