@@ -65,6 +65,15 @@ const char* pinn_last_error(pinn_handle* h);
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t pinn_launch_count(pinn_handle* h);
 
+/* Which implementation of the fused step kernel runs (same results to fp32 rounding, same interface):
+ *  PINN_ENGINE_TCGEN05 (default) - skinny mat-vecs as M=128 TF32 tcgen05.mma with activations in tensor memory (3xTF32);
+ *  PINN_ENGINE_FFMA              - the same mat-vecs as FFMA chains (kept for A/B measurement).
+ * The environment variable PINN_B200_ENGINE=ffma|tcgen05 selects the initial value at pinn_create. */
+#define PINN_ENGINE_FFMA 0
+#define PINN_ENGINE_TCGEN05 1
+int pinn_set_engine(pinn_handle* h, int engine);
+int pinn_get_engine(pinn_handle* h);
+
 /* Optional timing of the fused step kernel alone (bench.py's roofline figure): between begin and collect
  * every pinn_loss_fwd_bwd brackets its step-kernel launch with CUDA events on the caller's stream;
  * collect synchronises them and returns the summed duration and the number of launches. */

@@ -9,7 +9,7 @@ _LIB_NAME = "libpinn_b200.so"
 
 EXPORTS = [
     "pinn_version", "pinn_theta_size", "pinn_theta_offsets", "pinn_create", "pinn_destroy", "pinn_last_error",
-    "pinn_launch_count", "pinn_profile_begin", "pinn_profile_collect", "pinn_loss_fwd_bwd", "pinn_fields", "pinn_loss_fwd_bwd_host",
+    "pinn_launch_count", "pinn_set_engine", "pinn_get_engine", "pinn_profile_begin", "pinn_profile_collect", "pinn_loss_fwd_bwd", "pinn_fields", "pinn_loss_fwd_bwd_host",
 ]
 
 
@@ -49,6 +49,10 @@ def lib():
         L.pinn_last_error.restype = ctypes.c_char_p
         L.pinn_launch_count.argtypes = [vp]
         L.pinn_launch_count.restype = i64
+        L.pinn_set_engine.argtypes = [vp, i32]
+        L.pinn_set_engine.restype = i32
+        L.pinn_get_engine.argtypes = [vp]
+        L.pinn_get_engine.restype = i32
         L.pinn_profile_begin.argtypes = [vp]
         L.pinn_profile_begin.restype = i32
         L.pinn_profile_collect.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
@@ -92,6 +96,15 @@ class Handle:
 
     def launch_count(self):
         return int(self.L.pinn_launch_count(self.h))
+
+    ENGINES = {"ffma": 0, "tcgen05": 1}
+
+    def set_engine(self, name):
+        """'tcgen05' (default) or 'ffma': which implementation of the fused step kernel runs."""
+        self.check(self.L.pinn_set_engine(self.h, self.ENGINES[name]), "pinn_set_engine")
+
+    def get_engine(self):
+        return {v: k for k, v in self.ENGINES.items()}[int(self.L.pinn_get_engine(self.h))]
 
     def profile_begin(self):
         self.check(self.L.pinn_profile_begin(self.h), "pinn_profile_begin")

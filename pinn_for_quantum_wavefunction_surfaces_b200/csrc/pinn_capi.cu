@@ -1,5 +1,6 @@
 // C ABI of the PINN hot path (see include/pinn_b200.h for the contract).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -31,6 +32,7 @@ struct pinn_handle {
   cudaStream_t s_copy = nullptr, s_main = nullptr;
   cudaEvent_t ev_copy = nullptr;
   int64_t launches = 0;
+  int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
   bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -81,6 +83,10 @@ int pinn_create(int device, pinn_handle** out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->max_rows = h->sm_count * 8;
+  if (const char* e = getenv("PINN_B200_ENGINE")) {
+    if (!strcmp(e, "ffma")) h->engine = PINN_ENGINE_FFMA;
+    else if (!strcmp(e, "tcgen05")) h->engine = PINN_ENGINE_TCGEN05;
+  }
   CU(h, cudaMalloc(&h->wts, sizeof(Wts)));
   CU(h, cudaMalloc(&h->theta_dev, NPART * sizeof(float)));
   CU(h, cudaMalloc(&h->weights_dev, 4 * sizeof(double)));
@@ -113,6 +119,15 @@ int pinn_destroy(pinn_handle* h) {
 
 const char* pinn_last_error(pinn_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int64_t pinn_launch_count(pinn_handle* h) { return h ? h->launches : 0; }
+
+int pinn_set_engine(pinn_handle* h, int engine) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (engine != PINN_ENGINE_FFMA && engine != PINN_ENGINE_TCGEN05) return fail(h, PINN_EINVAL, "pinn_set_engine: unknown engine");
+  h->engine = engine;
+  return 0;
+}
+int pinn_get_engine(pinn_handle* h) { return h ? h->engine : PINN_EINVAL; }
 
 int pinn_profile_begin(pinn_handle* h) {
   if (!h) return PINN_EINVAL;
@@ -147,9 +162,14 @@ static int variant_coef(int variant, VariantCoef* vc, int* nev) {
 }
 
 static int grid_for(pinn_handle* h, long long n) {
+  // both engines give a persistent CTA 4 groups x 32 points per round
   const long long tiles = (n + 31) / 32;
   const long long want = (tiles + step_groups() - 1) / step_groups();
   return (int)(want < h->sm_count ? (want < 1 ? 1 : want) : h->sm_count);
+}
+
+static cudaError_t launch_step_any(pinn_handle* h, int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
+  return h->engine == PINN_ENGINE_TCGEN05 ? launch_step_tc(nev, train, p, grid, st) : launch_step(nev, train, p, grid, st);
 }
 
 int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
@@ -190,7 +210,7 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
     e1 = h->ev_pool[h->ev_used++];
     CU(h, cudaEventRecord(e0, st));
   }
-  CU(h, launch_step(nev, true, p, grid, st));
+  CU(h, launch_step_any(h, nev, true, p, grid, st));
   if (e1) CU(h, cudaEventRecord(e1, st));
   h->launches++;
   CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, st));
@@ -214,7 +234,7 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const voi
   p.x = x; p.y = y; p.z = z; p.R = R; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.psi = psi; p.lap = lap; p.hpsi = hpsi; p.res = res; p.E_out = E;
   CU(h, launch_prep(theta, h->wts, st));
-  CU(h, launch_step(nev, false, p, grid_for(h, n), st));
+  CU(h, launch_step_any(h, nev, false, p, grid_for(h, n), st));
   h->launches += 2;
   return 0;
 }

@@ -1,5 +1,6 @@
 // Shared constants and small device helpers of the PINN hot-path kernels (sm_100a).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -22,20 +23,36 @@ enum : int {
 
 // Weights as the kernels want them, built once per step by prep_weights_kernel and
 // bulk-copied (TMA, cp.async.bulk) into shared memory by every CTA.
-struct alignas(16) Wts {
+struct alignas(128) Wts {
   float w0[NH], w1[NH], b1[NH];          // W1[:,0], W1[:,1], b1
   float ww00[NH], ww01[NH], ww11[NH];    // w0^2, w0*w1, w1^2  (second-order channel)
-  float W2[NH * NH];                     // [j][k]  forward rows
-  float W2T[NH * NH];                    // [k][j]  reverse-sweep rows
   float b2[NH], wo[NH];
   float WE1[NE], bE1[NE];
-  float WE2[NE * NE];                    // [j][k]
-  float WE2T[NE * NE];                   // [k][j]
   float bE2[NE], wE[NE];
   float WgL[12], bgL[12], wg[12];        // 10 used
   float bo, bE, bg, pad0;
+  float pad1[24];                        // keeps the operand images below 128-byte aligned
+  // ---- tcgen05 B operands (pinn_step_tc.cu): [hi | lo] TF32 split, K-major canonical no-swizzle layout
+  //      (8-row x 16-byte core matrices; see umma_off()) ----
+  float BS[2][NH * NH];                  // n = j        : W2[j][k]                      (A = s)
+  float BSP[2][2 * NH * NH];             // n = c*16 + j : W2[j][k] * {w0,w1}[k]         (A = s')
+  float BSPP[2][3 * NH * NH];            // n = c*16 + j : W2[j][k] * {w0^2,w0w1,w1^2}[k] (A = s'')
+  float BWT[2][NH * NH];                 // n = k        : W2[j][k], K index = j          (reverse sweep)
+  float BE[2][NE * NE];                  // n = j        : WE2[j][k]
+  float BET[2][NE * NE];                 // n = k        : WE2[j][k], K index = j
+  // ---- FFMA engine only (pinn_kernels.cu); the tcgen05 kernel does not stage these ----
+  float W2[NH * NH];                     // [j][k]  forward rows
+  float W2T[NH * NH];                    // [k][j]  reverse-sweep rows
+  float WE2[NE * NE];                    // [j][k]
+  float WE2T[NE * NE];                   // [k][j]
 };
+// offset (floats) of element (n,k) of an N x K operand in the canonical K-major no-swizzle layout:
+// 16-byte K chunks strided by LBO = 128*(N/8) bytes, 8-row groups strided by SBO = 128 bytes
+__host__ __device__ constexpr int umma_off(int n, int k, int N) {
+  return (k / 4) * (32 * (N / 8)) + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
+}
 static_assert(sizeof(Wts) % 16 == 0, "Wts must be a multiple of 16 bytes for cp.async.bulk");
+static_assert(offsetof(Wts, BS) % 128 == 0 && offsetof(Wts, W2) % 16 == 0, "operand images must stay aligned");
 
 struct VariantCoef {  // res = cL*lap(psi) + cV*(1/r1+1/r2)*psi + cE*E*psi ; N = sN * sum(evals) + bo
   float sN, cL, cV, cE;

@@ -1,0 +1,142 @@
+// Device helpers shared by the FFMA step kernel (pinn_kernels.cu) and the tcgen05 step kernel (pinn_step_tc.cu).
+#pragma once
+#include "pinn_common.cuh"
+#include "pinn_launch.h"
+
+namespace pinn {
+
+// Per-point stash rows live in shared memory, one row per lane (= point): 64 floats for an MLP warp
+// (4 Taylor channels x 16), 32 for the E-net warp.  Rows are NOT padded; instead the column index is
+// XOR-swizzled with 8*(row&3), which makes the mma fragment loads (rows t / t+4, columns g / g+8)
+// conflict free and keeps float4 groups intact.
+constexpr int ROWH = 64;
+constexpr int ROWE = 32;
+constexpr int EVAL_STASH = 2 * 32 * ROWH;  // floats: Hs + Gs
+constexpr int ENET_STASH = 2 * 32 * ROWE;  // floats: E1s + Vs
+
+__device__ __forceinline__ int swz(int row) { return (row & 3) << 3; }
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sigmoid = 1 / (1 + 2^(-u log2 e)): FMUL + MUFU.EX2 + FADD + MUFU.RCP (the .ftz forms skip the denormal fix-up code;
+// saturates to 0 / 1 for large |u|)
+__device__ __forceinline__ float sigm(float u) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -1.4426950408889634f));
+  return rcp_approx(1.0f + e);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 3xTF32: x = hi + lo.  The tensor cores read the upper 19 bits of an fp32 operand (they truncate; measured with
+// tools/microbench/umma_ts.cu), so hi is x ROUNDED to nearest TF32 (add half an ulp, clear the low 13 bits), lo = x - hi is
+// exact in fp32, and lo gets half an ulp added so that the hardware truncation rounds it to nearest as well.  Unbiased,
+// |error| <= ~2^-22 per product instead of the ~2^-20 (always towards zero) of a plain mask split.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += a*b with fp32 accuracy: big*big + big*small + small*big (small*small ~2^-22 dropped)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
+// Column sum over the 32 rows (points) of a swizzled stash: lane sums column `col`.
+template <int ROW>
+__device__ __forceinline__ float colsum(const float* __restrict__ base, int col) {
+  const float* p0 = base + col;
+  const float* p1 = base + ROW + (col ^ 8);
+  const float* p2 = base + 2 * ROW + (col ^ 16);
+  const float* p3 = base + 3 * ROW + (col ^ 24);
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 2
+  for (int p = 0; p < 32; p += 4) {
+    s0 += p0[p * ROW]; s1 += p1[p * ROW]; s2 += p2[p * ROW]; s3 += p3[p * ROW];
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+// Weighted column sums: returns sum_p base[p][col] and sum_p wgt_p * base[p][col] (wgt = per-lane value of row p)
+template <int ROW>
+__device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col, float wgt, float& plain, float& weighted) {
+  float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
+#pragma unroll 2
+  for (int p = 0; p < 32; p += 4) {
+    const float v0 = base[(p + 0) * ROW + col], v1 = base[(p + 1) * ROW + (col ^ 8)];
+    const float v2 = base[(p + 2) * ROW + (col ^ 16)], v3 = base[(p + 3) * ROW + (col ^ 24)];
+    s0 += v0; s1 += v1; s0 += v2; s1 += v3;
+    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 0), v0, t0);
+    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 1), v1, t1);
+    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 2), v2, t0);
+    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 3), v3, t1);
+  }
+  plain = s0 + s1;
+  weighted = t0 + t1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-point geometry (poc/main.py:101-108, 269-284; train.py:41-44) and the coefficients of the
+// second-order operator D (oracle/closed_form.py:geometry)
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+  float f1, f2, ir1, ir2, al1, al2, al11, al12, al22;
+  float R;
+};
+
+__device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) {
+  float dx1, dx2, y, z, R;
+  if (p.in_f64) {
+    const double xd = ((const double*)p.x)[i], Rd = ((const double*)p.R)[i];
+    dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
+    dx2 = (float)(xd + Rd);
+    y = (float)((const double*)p.y)[i];
+    z = (float)((const double*)p.z)[i];
+    R = (float)Rd;
+  } else {
+    const float xf = ((const float*)p.x)[i];
+    R = ((const float*)p.R)[i];
+    dx1 = xf - R;
+    dx2 = xf + R;
+    y = ((const float*)p.y)[i];
+    z = ((const float*)p.z)[i];
+  }
+  Geom g;
+  const float yz = fmaf(y, y, z * z);
+  const float q1 = fmaf(dx1, dx1, yz), q2 = fmaf(dx2, dx2, yz);
+  g.ir1 = rsqrtf(q1);
+  g.ir2 = rsqrtf(q2);
+  const float r1 = q1 * g.ir1, r2 = q2 * g.ir2;
+  g.f1 = __expf(-r1);
+  g.f2 = __expf(-r2);
+  const float c12 = fmaf(dx1, dx2, yz) * g.ir1 * g.ir2;
+  g.al1 = g.f1 * fmaf(-2.0f, g.ir1, 1.0f);
+  g.al2 = g.f2 * fmaf(-2.0f, g.ir2, 1.0f);
+  g.al11 = g.f1 * g.f1;
+  g.al22 = g.f2 * g.f2;
+  g.al12 = 2.0f * g.f1 * g.f2 * c12;
+  g.R = R;
+  return g;
+}
+
+#define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
+#define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))
+
+}  // namespace pinn

@@ -21,135 +21,10 @@
 //     transposing shuffle butterfly (32 values -> one per lane).
 //   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
 //     in double precision in a fixed order (deterministic).
-#include "pinn_common.cuh"
-#include "pinn_launch.h"
+#include "pinn_device.cuh"
 
 namespace pinn {
 
-// Per-point stash rows live in shared memory, one row per lane (= point): 64 floats for an MLP warp
-// (4 Taylor channels x 16), 32 for the E-net warp.  Rows are NOT padded; instead the column index is
-// XOR-swizzled with 8*(row&3), which makes the mma fragment loads (rows t / t+4, columns g / g+8)
-// conflict free and keeps float4 groups intact.
-constexpr int ROWH = 64;
-constexpr int ROWE = 32;
-constexpr int EVAL_STASH = 2 * 32 * ROWH;  // floats: Hs + Gs
-constexpr int ENET_STASH = 2 * 32 * ROWE;  // floats: E1s + Vs
-
-__device__ __forceinline__ int swz(int row) { return (row & 3) << 3; }
-
-// ---------------------------------------------------------------------------------------------
-// small PTX helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sigm(float u) { return rcp_approx(1.0f + __expf(-u)); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void named_barrier(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// 3xTF32: x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// c += a*b with fp32 accuracy: big*big + big*small + small*big (small*small ~2^-22 dropped)
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                           uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma_tf32(c, al, bh0, bh1);
-  mma_tf32(c, ah, bl0, bl1);
-  mma_tf32(c, ah, bh0, bh1);
-}
-
-// Column sum over the 32 rows (points) of a swizzled stash: lane sums column `col`.
-template <int ROW>
-__device__ __forceinline__ float colsum(const float* __restrict__ base, int col) {
-  const float* p0 = base + col;
-  const float* p1 = base + ROW + (col ^ 8);
-  const float* p2 = base + 2 * ROW + (col ^ 16);
-  const float* p3 = base + 3 * ROW + (col ^ 24);
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll 2
-  for (int p = 0; p < 32; p += 4) {
-    s0 += p0[p * ROW]; s1 += p1[p * ROW]; s2 += p2[p * ROW]; s3 += p3[p * ROW];
-  }
-  return (s0 + s1) + (s2 + s3);
-}
-// Weighted column sums: returns sum_p base[p][col] and sum_p wgt_p * base[p][col] (wgt = per-lane value of row p)
-template <int ROW>
-__device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col, float wgt, float& plain, float& weighted) {
-  float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
-#pragma unroll 2
-  for (int p = 0; p < 32; p += 4) {
-    const float v0 = base[(p + 0) * ROW + col], v1 = base[(p + 1) * ROW + (col ^ 8)];
-    const float v2 = base[(p + 2) * ROW + (col ^ 16)], v3 = base[(p + 3) * ROW + (col ^ 24)];
-    s0 += v0; s1 += v1; s0 += v2; s1 += v3;
-    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 0), v0, t0);
-    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 1), v1, t1);
-    t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 2), v2, t0);
-    t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 3), v3, t1);
-  }
-  plain = s0 + s1;
-  weighted = t0 + t1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// per-point geometry (poc/main.py:101-108, 269-284; train.py:41-44) and the coefficients of the
-// second-order operator D (oracle/closed_form.py:geometry)
-// ---------------------------------------------------------------------------------------------
-struct Geom {
-  float f1, f2, ir1, ir2, al1, al2, al11, al12, al22;
-  float R;
-};
-
-__device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) {
-  float dx1, dx2, y, z, R;
-  if (p.in_f64) {
-    const double xd = ((const double*)p.x)[i], Rd = ((const double*)p.R)[i];
-    dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
-    dx2 = (float)(xd + Rd);
-    y = (float)((const double*)p.y)[i];
-    z = (float)((const double*)p.z)[i];
-    R = (float)Rd;
-  } else {
-    const float xf = ((const float*)p.x)[i];
-    R = ((const float*)p.R)[i];
-    dx1 = xf - R;
-    dx2 = xf + R;
-    y = ((const float*)p.y)[i];
-    z = ((const float*)p.z)[i];
-  }
-  Geom g;
-  const float yz = fmaf(y, y, z * z);
-  const float q1 = fmaf(dx1, dx1, yz), q2 = fmaf(dx2, dx2, yz);
-  g.ir1 = rsqrtf(q1);
-  g.ir2 = rsqrtf(q2);
-  const float r1 = q1 * g.ir1, r2 = q2 * g.ir2;
-  g.f1 = __expf(-r1);
-  g.f2 = __expf(-r2);
-  const float c12 = fmaf(dx1, dx2, yz) * g.ir1 * g.ir2;
-  g.al1 = g.f1 * fmaf(-2.0f, g.ir1, 1.0f);
-  g.al2 = g.f2 * fmaf(-2.0f, g.ir2, 1.0f);
-  g.al11 = g.f1 * g.f1;
-  g.al22 = g.f2 * g.f2;
-  g.al12 = 2.0f * g.f1 * g.f2 * c12;
-  g.R = R;
-  return g;
-}
-
-#define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
-#define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))
 
 // ---------------------------------------------------------------------------------------------
 // base MLP, one evaluation at (a,b): 4-channel Taylor forward (value, d/da, d/db, D)
@@ -800,6 +675,30 @@ __global__ void prep_weights_kernel(const float* __restrict__ th, Wts* __restric
     out->wg[i] = in ? th[O_WG + i] : 0.0f;
   }
   if (t == 0) { out->bo = th[O_BO]; out->bE = th[O_BE]; out->bg = th[O_BG]; out->pad0 = 0.0f; }
+  // ---- tcgen05 operand images: value -> (hi, lo) TF32 pair ----
+  auto put = [](float* hi, float* lo, int off, float v) {
+    uint32_t h, l;
+    split_tf32(v, h, l);  // round-to-nearest split, see pinn_device.cuh
+    hi[off] = __uint_as_float(h);
+    lo[off] = __uint_as_float(l);
+  };
+  for (int i = t; i < NH * NH; i += blockDim.x) {
+    const int j = i / NH, k = i % NH;
+    const float wjk = th[O_W2 + i];
+    const float a = th[O_W1 + 2 * k], b = th[O_W1 + 2 * k + 1];
+    put(out->BS[0], out->BS[1], umma_off(j, k, NH), wjk);
+    put(out->BSP[0], out->BSP[1], umma_off(j, k, 2 * NH), wjk * a);
+    put(out->BSP[0], out->BSP[1], umma_off(NH + j, k, 2 * NH), wjk * b);
+    put(out->BSPP[0], out->BSPP[1], umma_off(j, k, 3 * NH), wjk * (a * a));
+    put(out->BSPP[0], out->BSPP[1], umma_off(NH + j, k, 3 * NH), wjk * (a * b));
+    put(out->BSPP[0], out->BSPP[1], umma_off(2 * NH + j, k, 3 * NH), wjk * (b * b));
+    put(out->BWT[0], out->BWT[1], umma_off(k, j, NH), wjk);
+  }
+  for (int i = t; i < NE * NE; i += blockDim.x) {
+    const int j = i / NE, k = i % NE;
+    put(out->BE[0], out->BE[1], umma_off(j, k, NE), th[O_WE2 + i]);
+    put(out->BET[0], out->BET[1], umma_off(k, j, NE), th[O_WE2 + i]);
+  }
 }
 
 // counts of the two boundary sets -> weights {1/n, 1/cnt1, 1/cnt2} (only when the caller passes no weights)

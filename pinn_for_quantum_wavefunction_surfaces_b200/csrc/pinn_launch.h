@@ -24,6 +24,8 @@ struct StepParams {
 
 cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
 int step_groups();
+// tcgen05 engine (pinn_step_tc.cu): super-tiles of 128 points, one persistent CTA per SM
+cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
 cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st);
 cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st);
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,

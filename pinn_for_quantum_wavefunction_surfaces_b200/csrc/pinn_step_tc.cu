@@ -1,0 +1,868 @@
+// Fused PINN residual-and-gradient kernel, tcgen05 engine (B200, sm_100a).
+//
+// Same mathematics and the same role decomposition as pinn_kernels.cu (oracle/closed_form.py is the
+// specification; poc/main.py:247-303, 82-120, 341-355 and train.py:41-57 are what it replaces), but the
+// four mat-vec families of a tile
+//     base-MLP layer 2 forward      V = W2 h        (4 Taylor channels)
+//     base-MLP layer 2 reverse      hbar = W2^T vbar (4 channels)
+//     E-net layer 2 forward / reverse (32 x 32)
+// run on the 5th-generation tensor cores instead of FFMA chains:
+//   * a CTA works on a SUPER-TILE of 128 collocation points: 4 groups x 32 points, thread = point =
+//     TMEM lane.  Warps are specialised by role as before (one warpgroup per MLP evaluation, one for
+//     E-net + gate); the 4 warps of a role form the 128 rows of an M=128 tcgen05.mma.
+//   * every thread writes its row of the A operand (activations, split x = hi + lo with hi = the 19 bits
+//     the tensor core reads) straight from registers into TENSOR MEMORY with tcgen05.st; the B operands
+//     (weights, split the same way, canonical K-major layout) sit in shared memory, staged once per CTA
+//     by a TMA bulk copy; D accumulates in TMEM and comes back with tcgen05.ld.  3xTF32
+//     (lo*hi + hi*lo + hi*hi) keeps fp32 accuracy (tools/microbench/umma_ts.cu: 4e-7 relative).
+//   * the forward uses the linearity of the Taylor channels in the layer-1 quantities: with A = {s, s', s''}
+//     (3 x 16 columns instead of 4 x 16) and the pre-multiplied operand images BS/BSP/BSPP of
+//     prep_weights_kernel the 4-channel product needs 18 instead of 24 MMAs.
+//   * an M=128, K=8 TF32 MMA costs ~47 cycles for any N <= 64 (measured), so the tensor pipe is busy
+//     ~40 cycles per point and overlaps the element-wise work of the other roles; the weight-gradient
+//     contractions (K = points) stay on mma.sync, reading the shared-memory stash, and are issued while
+//     the reverse-sweep MMAs are in flight.
+#include "pinn_device.cuh"
+
+namespace pinn {
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM / mbarrier PTX
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+// shared-memory operand descriptor: K-major, no swizzle, N rows (see umma_off): LBO = 128*(N/8) B, SBO = 128 B
+__device__ __forceinline__ uint64_t tc_bdesc(uint32_t saddr, uint32_t N) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)N << 16) | ((uint64_t)8 << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// D (+)= (a_hi + a_lo) * (B_hi + B_lo) without the lo*lo term
+__device__ __forceinline__ void tc_mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t N,
+                                        uint32_t idesc, bool first) {
+  tc_mma(d, a_lo, tc_bdesc(b_hi, N), idesc, first ? 0u : 1u);
+  tc_mma(d, a_hi, tc_bdesc(b_lo, N), idesc, 1u);
+  tc_mma(d, a_hi, tc_bdesc(b_hi, N), idesc, 1u);
+}
+
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// split 16 values and store them as the hi / lo halves of an A operand row
+__device__ __forceinline__ void tc_st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    split_tf32(x[i], hi[i], lo[i]);
+  }
+  tc_st16(t_hi, hi);
+  tc_st16(t_lo, lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMEM column map (512 columns x 128 lanes; lane = point of the super-tile)
+//   MLP role r (r = 0,1): columns [192 r, 192 r + 192)
+//     forward : A = s hi|s' hi|s'' hi|s lo|s' lo|s'' lo (6 x 16)   D = V0 (16) | V1,V2 (32) | P00,P01,P11 (48)
+//     reverse : A = vbar hi (4 x 16) | vbar lo (4 x 16)            D = hbar (4 x 16)
+//   E-net role: columns [384, 480): A = e1 / vbar hi (32) | lo (32), D (32)
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t TC_MLP_COLS = 192, TC_E_BASE = 384;
+constexpr uint32_t F_S_HI = 0, F_SP_HI = 16, F_SPP_HI = 32, F_S_LO = 48, F_SP_LO = 64, F_SPP_LO = 80;
+constexpr uint32_t F_V0 = 96, F_V12 = 112, F_P = 144;
+constexpr uint32_t B_VB_HI = 0, B_VB_LO = 64, B_HB = 128;
+constexpr uint32_t E_A_HI = 0, E_A_LO = 32, E_D = 64;
+
+constexpr size_t WTS_TC_BYTES = offsetof(Wts, W2);  // everything the tcgen05 kernel stages
+static_assert(WTS_TC_BYTES % 128 == 0, "staged weight image must keep the buffers behind it aligned");
+
+template <int NEV>
+__host__ __device__ constexpr int tc_group_stash_floats() { return NEV * EVAL_STASH + ENET_STASH; }
+template <int NEV>
+__host__ __device__ constexpr size_t tc_smem_bytes() {
+  return WTS_TC_BYTES + 64 /*mbarriers + tmem base*/ + sizeof(float2) * 4 * 2 * 3 * 32 + sizeof(float) * 4 * tc_group_stash_floats<NEV>();
+}
+
+struct TcCtx {
+  uint32_t tbase;      // TMEM base address of the allocation
+  uint32_t tlane;      // tbase + (32 * group) << 16: this warp's lane quarter
+  uint32_t mbar;       // shared address of this role's mbarrier
+  uint32_t phase;      // parity of the next completion
+  int bar_id;          // named barrier of this role (128 threads)
+  bool issuer;         // the one thread of the role that issues its MMAs
+  uint32_t wts_saddr;  // shared address of the weight image
+};
+
+__device__ __forceinline__ void tc_role_sync(const TcCtx& c) {
+  tc_wait_st();
+  tc_fence_before();
+  named_barrier(c.bar_id, 128);
+}
+__device__ __forceinline__ void tc_wait_mma(TcCtx& c) {
+  mbar_wait(c.mbar, c.phase);
+  c.phase ^= 1u;
+  tc_fence_after();
+}
+
+// ---------------------------------------------------------------------------------------------
+// base MLP, forward (oracle/closed_form.py:mlp_fwd)
+// ---------------------------------------------------------------------------------------------
+template <bool STASH>
+__device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t cb, float a, float b, float al1, float al2,
+                                               float al11, float al12, float al22, float* __restrict__ Hrow,
+                                               float* __restrict__ Grow, int sx, float& Nv, float& Dv) {
+  {
+    float s_[NH], sp_[NH], spp_[NH];
+#pragma unroll
+    for (int k4 = 0; k4 < NH; k4 += 4) {
+      const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]), b1v = LD4(&w.b1[k4]);
+      const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+      const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float u = fmaf(a, w0a[i], fmaf(b, w1a[i], b1a[i]));
+        const float s = sigm(u);
+        const float sp = fmaf(-s, s, s);            // s(1-s)
+        const float spp = fmaf(-2.0f * s, sp, sp);  // s'(1-2s)
+        s_[k4 + i] = s; sp_[k4 + i] = sp; spp_[k4 + i] = spp;
+      }
+      if (STASH) {
+        // the 4-channel h of the weight-gradient contraction and of the reverse sweep
+        const float4 q00 = LD4(&w.ww00[k4]), q01 = LD4(&w.ww01[k4]), q11 = LD4(&w.ww11[k4]);
+        const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
+        const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+        float h1[4], h2[4], h3[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float d1 = fmaf(al1, w0a[i], al2 * w1a[i]);
+          const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
+          h1[i] = sp_[k4 + i] * w0a[i];
+          h2[i] = sp_[k4 + i] * w1a[i];
+          h3[i] = fmaf(sp_[k4 + i], d1, spp_[k4 + i] * q);
+        }
+        ST4(&Hrow[(0 * NH + k4) ^ sx], s_[k4], s_[k4 + 1], s_[k4 + 2], s_[k4 + 3]);
+        ST4(&Hrow[(1 * NH + k4) ^ sx], h1[0], h1[1], h1[2], h1[3]);
+        ST4(&Hrow[(2 * NH + k4) ^ sx], h2[0], h2[1], h2[2], h2[3]);
+        ST4(&Hrow[(3 * NH + k4) ^ sx], h3[0], h3[1], h3[2], h3[3]);
+      }
+    }
+    const uint32_t t0 = c.tlane + cb;
+    tc_st_split16(t0 + F_S_HI, t0 + F_S_LO, s_);
+    tc_st_split16(t0 + F_SP_HI, t0 + F_SP_LO, sp_);
+    tc_st_split16(t0 + F_SPP_HI, t0 + F_SPP_LO, spp_);
+  }
+  tc_role_sync(c);
+  if (c.issuer) {
+    tc_fence_after();
+    const uint32_t d = c.tbase + cb;
+    const uint32_t bs = c.wts_saddr + (uint32_t)offsetof(Wts, BS), bsp = c.wts_saddr + (uint32_t)offsetof(Wts, BSP);
+    const uint32_t bspp = c.wts_saddr + (uint32_t)offsetof(Wts, BSPP);
+#pragma unroll
+    for (uint32_t ks = 0; ks < 2; ks++) {
+      // one K step = 8 values = two 16-byte chunks = 2*LBO = 32*N bytes
+      tc_mma3(d + F_V0, d + F_S_HI + 8 * ks, d + F_S_LO + 8 * ks, bs + ks * 32 * 16, bs + 4 * NH * NH + ks * 32 * 16, 16,
+              tc_idesc(16), ks == 0);
+      tc_mma3(d + F_V12, d + F_SP_HI + 8 * ks, d + F_SP_LO + 8 * ks, bsp + ks * 32 * 32, bsp + 4 * 2 * NH * NH + ks * 32 * 32,
+              32, tc_idesc(32), ks == 0);
+      tc_mma3(d + F_P, d + F_SPP_HI + 8 * ks, d + F_SPP_LO + 8 * ks, bspp + ks * 32 * 48,
+              bspp + 4 * 3 * NH * NH + ks * 32 * 48, 48, tc_idesc(48), ks == 0);
+    }
+    tc_commit(c.mbar);
+  }
+  __syncwarp();
+  tc_wait_mma(c);
+
+  float accN = 0.0f, accD = 0.0f;
+#pragma unroll
+  for (int j8 = 0; j8 < NH; j8 += 8) {
+    float V0[8], V1[8], V2[8], P00[8], P01[8], P11[8];
+    const uint32_t t0 = c.tlane + cb;
+    tc_ld8(t0 + F_V0 + j8, V0);
+    tc_ld8(t0 + F_V12 + j8, V1);
+    tc_ld8(t0 + F_V12 + NH + j8, V2);
+    tc_ld8(t0 + F_P + j8, P00);
+    tc_ld8(t0 + F_P + NH + j8, P01);
+    tc_ld8(t0 + F_P + 2 * NH + j8, P11);
+    tc_wait_ld();
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4 += 4) {
+      const float4 b2v = LD4(&w.b2[j8 + j4]), wov = LD4(&w.wo[j8 + j4]);
+      const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
+      float tt[4], va[4], vb[4], vD[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int j = j4 + i;
+        const float v0 = V0[j] + b2a[i], v1 = V1[j], v2 = V2[j];
+        const float v3 = fmaf(al1, v1, fmaf(al2, v2, fmaf(al11, P00[j], fmaf(al12, P01[j], al22 * P11[j]))));
+        const float t = sigm(v0);
+        const float tp = fmaf(-t, t, t);
+        const float tpp = fmaf(-2.0f * t, tp, tp);
+        const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
+        const float gD = fmaf(tp, v3, tpp * Q);
+        accN = fmaf(woa[i], t, accN);
+        accD = fmaf(woa[i], gD, accD);
+        tt[i] = t; va[i] = v1; vb[i] = v2; vD[i] = v3;
+      }
+      if (STASH) {
+        ST4(&Grow[(0 * NH + j8 + j4) ^ sx], tt[0], tt[1], tt[2], tt[3]);
+        ST4(&Grow[(1 * NH + j8 + j4) ^ sx], va[0], va[1], va[2], va[3]);
+        ST4(&Grow[(2 * NH + j8 + j4) ^ sx], vb[0], vb[1], vb[2], vb[3]);
+        ST4(&Grow[(3 * NH + j8 + j4) ^ sx], vD[0], vD[1], vD[2], vD[3]);
+      }
+    }
+  }
+  Nv = accN;
+  Dv = accD;
+}
+
+// persistent per-lane accumulators of a warp; one layout for both roles so that the registers are shared
+//   MLP warp  : c[0][nt] = mma.sync C fragments of dW2 (16x16), nt = 0,1
+//               s0: lane<16 db2[lane] | dwo[lane-16];  s1: lane<16 dW1[lane][0] | dW1[lane-16][1];
+//               s2: lane<16 db1[lane] | extra[lane-16] (loss sums, role 0)
+//   E-net warp: c[mt][nt] = C fragments of dWE2 (32x32);
+//               s0..s4 = dwE[lane], dbE2[lane], dWE1[lane], dbE1[lane], {dWgL,dbgL,dwg,dbg,dbE}[lane]
+struct TcAcc {
+  float c[2][4][4];
+  float s0, s1, s2, s3, s4;
+};
+using TcMlpAcc = TcAcc;
+using TcEnetAcc = TcAcc;
+
+// Reverse sweep of one MLP evaluation (oracle/closed_form.py:mlp_bwd) for the seeds lamN, lamD
+__device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t cb, float a, float b, float al1, float al2,
+                                                float al11, float al12, float al22, float lamN, float lamD,
+                                                float* __restrict__ Hs, float* __restrict__ Gs, int lane,
+                                                const float (&extra)[8], TcMlpAcc& acc) {
+  const int sx = swz(lane);
+  float* Hrow = Hs + lane * ROWH;
+  float* Grow = Gs + lane * ROWH;
+  float dwo[NH];
+  {
+    float vbar[4][NH];
+#pragma unroll
+    for (int j4 = 0; j4 < NH; j4 += 4) {
+      const float4 tv = LD4(&Grow[(0 * NH + j4) ^ sx]), av = LD4(&Grow[(1 * NH + j4) ^ sx]);
+      const float4 bv = LD4(&Grow[(2 * NH + j4) ^ sx]), dv = LD4(&Grow[(3 * NH + j4) ^ sx]);
+      const float4 wov = LD4(&w.wo[j4]);
+      const float ta[4] = {tv.x, tv.y, tv.z, tv.w}, vaa[4] = {av.x, av.y, av.z, av.w};
+      const float vba[4] = {bv.x, bv.y, bv.z, bv.w}, vDa[4] = {dv.x, dv.y, dv.z, dv.w};
+      const float woa[4] = {wov.x, wov.y, wov.z, wov.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int j = j4 + i;
+        const float t = ta[i], v1 = vaa[i], v2 = vba[i], v3 = vDa[i];
+        const float tp = fmaf(-t, t, t);
+        const float tpp = fmaf(-2.0f * t, tp, tp);
+        const float tppp = tp * fmaf(-6.0f, tp, 1.0f);
+        const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
+        const float gD = fmaf(tp, v3, tpp * Q);
+        const float tbar = lamN * woa[i], gDbar = lamD * woa[i];
+        dwo[j] = fmaf(lamN, t, lamD * gD);
+        const float c2 = gDbar * tpp;
+        vbar[3][j] = gDbar * tp;
+        vbar[1][j] = c2 * fmaf(2.0f * al11, v1, al12 * v2);
+        vbar[2][j] = c2 * fmaf(al12, v1, 2.0f * al22 * v2);
+        vbar[0][j] = fmaf(tbar, tp, gDbar * fmaf(tpp, v3, tppp * Q));
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ch++)
+        ST4(&Grow[(ch * NH + j4) ^ sx], vbar[ch][j4], vbar[ch][j4 + 1], vbar[ch][j4 + 2], vbar[ch][j4 + 3]);
+    }
+    const uint32_t t0 = c.tlane + cb;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) tc_st_split16(t0 + B_VB_HI + ch * NH, t0 + B_VB_LO + ch * NH, vbar[ch]);
+  }
+  tc_role_sync(c);  // (also orders the stash writes above before the fragment loads below: bar.sync)
+  if (c.issuer) {
+    tc_fence_after();
+    const uint32_t d = c.tbase + cb;
+    const uint32_t bw = c.wts_saddr + (uint32_t)offsetof(Wts, BWT);
+#pragma unroll
+    for (uint32_t ch = 0; ch < 4; ch++)
+#pragma unroll
+      for (uint32_t ks = 0; ks < 2; ks++)
+        tc_mma3(d + B_HB + ch * NH, d + B_VB_HI + ch * NH + 8 * ks, d + B_VB_LO + ch * NH + 8 * ks, bw + ks * 32 * 16,
+                bw + 4 * NH * NH + ks * 32 * 16, 16, tc_idesc(16), ks == 0);
+    tc_commit(c.mbar);
+  }
+  __syncwarp();
+
+  // ---- while the tensor core runs: dW2[j][k] += sum_{p,c} G[p][c][j] * H[p][c][k] (mma.sync, 3xTF32) ----
+  {
+    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ch++) {
+#pragma unroll
+      for (int po = 0; po < 4; po++) {
+        const float* Ga = Gs + (po * 8 + t) * ROWH;
+        const float* Gb = Ga + 4 * ROWH;
+        const float* Ha = Hs + (po * 8 + t) * ROWH;
+        const float* Hb = Ha + 4 * ROWH;
+        const int ca = (ch * NH + g) ^ tx, cbb = (ch * NH + g + 8) ^ tx;
+        uint32_t ah[4], al[4];
+        split_tf32(Ga[ca], ah[0], al[0]);
+        split_tf32(Ga[cbb], ah[1], al[1]);
+        split_tf32(Gb[ca], ah[2], al[2]);
+        split_tf32(Gb[cbb], ah[3], al[3]);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Ha[ca], bh0, bl0);
+        split_tf32(Hb[ca], bh1, bl1);
+        mma_3xtf32(acc.c[0][0], ah, al, bh0, bh1, bl0, bl1);
+        split_tf32(Ha[cbb], bh0, bl0);
+        split_tf32(Hb[cbb], bh1, bl1);
+        mma_3xtf32(acc.c[0][1], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  __syncwarp();  // all fragment loads done: channel 1..3 regions of the stash rows may be reused
+  // ---- db2 (= column sums of vbar channel 0) and dwo ----
+#pragma unroll
+  for (int j4 = 0; j4 < NH; j4 += 4) ST4(&Grow[(NH + j4) ^ sx], dwo[j4], dwo[j4 + 1], dwo[j4 + 2], dwo[j4 + 3]);
+  __syncwarp();
+  acc.s0 += colsum<ROWH>(Gs, lane);
+
+  // ---- hbar = W2^T vbar is in TMEM now: layer-1 reverse sweep ----
+  tc_wait_mma(c);
+#pragma unroll
+  for (int k8 = 0; k8 < NH; k8 += 8) {
+    float hb0[8], hb1[8], hb2[8], hb3[8];
+    const uint32_t t0 = c.tlane + cb + B_HB;
+    tc_ld8(t0 + 0 * NH + k8, hb0);
+    tc_ld8(t0 + 1 * NH + k8, hb1);
+    tc_ld8(t0 + 2 * NH + k8, hb2);
+    tc_ld8(t0 + 3 * NH + k8, hb3);
+    tc_wait_ld();
+#pragma unroll
+    for (int k4 = 0; k4 < 8; k4 += 4) {
+      const int kk = k8 + k4;
+      const float4 sv = LD4(&Hrow[kk ^ sx]);  // h channel 0 = s_k
+      const float4 w0v = LD4(&w.w0[kk]), w1v = LD4(&w.w1[kk]);
+      const float4 q00 = LD4(&w.ww00[kk]), q01 = LD4(&w.ww01[kk]), q11 = LD4(&w.ww11[kk]);
+      const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+      const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+      const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
+      const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+      float o0[4], o1[4], ob[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float h0 = hb0[k4 + i], h1 = hb1[k4 + i], h2 = hb2[k4 + i], h3 = hb3[k4 + i];
+        const float s = sa[i], w0 = w0a[i], w1 = w1a[i];
+        const float sp = fmaf(-s, s, s);
+        const float spp = fmaf(-2.0f * s, sp, sp);
+        const float sppp = sp * fmaf(-6.0f, sp, 1.0f);
+        const float d1 = fmaf(al1, w0, al2 * w1);
+        const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
+        const float ubar = fmaf(h0, sp, fmaf(fmaf(h1, w0, fmaf(h2, w1, h3 * d1)), spp, h3 * q * sppp));
+        o0[i] = fmaf(h1, sp, fmaf(h3, fmaf(sp, al1, spp * fmaf(2.0f * al11, w0, al12 * w1)), ubar * a));
+        o1[i] = fmaf(h2, sp, fmaf(h3, fmaf(sp, al2, spp * fmaf(al12, w0, 2.0f * al22 * w1)), ubar * b));
+        ob[i] = ubar;
+      }
+      ST4(&Hrow[(1 * NH + kk) ^ sx], o0[0], o0[1], o0[2], o0[3]);
+      ST4(&Hrow[(2 * NH + kk) ^ sx], o1[0], o1[1], o1[2], o1[3]);
+      ST4(&Hrow[(3 * NH + kk) ^ sx], ob[0], ob[1], ob[2], ob[3]);
+    }
+  }
+  ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
+  ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
+  __syncwarp();
+  acc.s1 += colsum<ROWH>(Hs, NH + lane);                              // columns 16..47: dw0 | dw1
+  acc.s2 += colsum<ROWH>(Hs, lane < 16 ? 3 * NH + lane : lane - 16);  // columns 48..63: db1 ; 0..15: extras
+  __syncwarp();
+}
+
+// loss sums only (fine-tune mode: no base-MLP reverse sweep); role 0
+__device__ __forceinline__ void tc_mlp_extras_only(float* __restrict__ Hs, int lane, const float (&extra)[8], TcMlpAcc& acc) {
+  const int sx = swz(lane);
+  float* Hrow = Hs + lane * ROWH;
+  __syncwarp();
+  ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
+  ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
+  __syncwarp();
+  const float v = colsum<ROWH>(Hs, lane & 7);
+  if (lane >= 16 && lane < 24) acc.s2 += v;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// E(R) network (poc/main.py:249-253; train.py:50-52) and gate (poc/main.py:262-264; train.py:48-49)
+// ---------------------------------------------------------------------------------------------
+template <bool STASH>
+__device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R, float* __restrict__ E1row,
+                                                 float* __restrict__ Vrow, int sx) {
+  const uint32_t t0 = c.tlane + TC_E_BASE;
+#pragma unroll
+  for (int k16 = 0; k16 < NE; k16 += 16) {
+    float e1[16];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const float4 wv = LD4(&w.WE1[k16 + k4]), bv = LD4(&w.bE1[k16 + k4]);
+      e1[k4 + 0] = sigm(fmaf(R, wv.x, bv.x));
+      e1[k4 + 1] = sigm(fmaf(R, wv.y, bv.y));
+      e1[k4 + 2] = sigm(fmaf(R, wv.z, bv.z));
+      e1[k4 + 3] = sigm(fmaf(R, wv.w, bv.w));
+      if (STASH) ST4(&E1row[(k16 + k4) ^ sx], e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
+    }
+    tc_st_split16(t0 + E_A_HI + k16, t0 + E_A_LO + k16, e1);
+  }
+  tc_role_sync(c);
+  if (c.issuer) {
+    tc_fence_after();
+    const uint32_t d = c.tbase + TC_E_BASE;
+    const uint32_t be = c.wts_saddr + (uint32_t)offsetof(Wts, BE);
+#pragma unroll
+    for (uint32_t ks = 0; ks < 4; ks++)
+      tc_mma3(d + E_D, d + E_A_HI + 8 * ks, d + E_A_LO + 8 * ks, be + ks * 32 * 32, be + 4 * NE * NE + ks * 32 * 32, 32,
+              tc_idesc(32), ks == 0);
+    tc_commit(c.mbar);
+  }
+  __syncwarp();
+  tc_wait_mma(c);
+  float E = w.bE;
+#pragma unroll
+  for (int j16 = 0; j16 < NE; j16 += 16) {
+    float v[16];
+    tc_ld16(t0 + E_D + j16, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 b2v = LD4(&w.bE2[j16 + j4]), wEv = LD4(&w.wE[j16 + j4]);
+      const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
+      float e2[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        e2[i] = sigm(v[j4 + i] + b2a[i]);
+        E = fmaf(wEa[i], e2[i], E);
+      }
+      if (STASH) ST4(&Vrow[(j16 + j4) ^ sx], e2[0], e2[1], e2[2], e2[3]);
+    }
+  }
+  return E;
+}
+
+__device__ __forceinline__ float tc_gate_forward(const Wts& w, float R) {
+  float g = w.bg;
+#pragma unroll
+  for (int i = 0; i < NL; i++) g = fmaf(w.wg[i], sigm(fmaf(R, w.WgL[i], w.bgL[i])), g);
+  return g;
+}
+
+__device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R, float Ebar, float gbar, bool gate_grads,
+                                                 float* __restrict__ E1s, float* __restrict__ Vs, int lane, TcEnetAcc& acc) {
+  const int sx = swz(lane);
+  float* E1row = E1s + lane * ROWE;
+  float* Vrow = Vs + lane * ROWE;
+  const uint32_t t0 = c.tlane + TC_E_BASE;
+  __syncwarp();
+  // ---- dwE[j] = sum_p Ebar_p e2[p][j] (Vs still holds e2) ----
+  {
+    float plain, weighted;
+    colsum_w<ROWE>(Vs, lane, Ebar, plain, weighted);
+    acc.s0 += weighted;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j16 = 0; j16 < NE; j16 += 16) {
+    float vbar[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 ev = LD4(&Vrow[(j16 + j4) ^ sx]), wEv = LD4(&w.wE[j16 + j4]);
+      const float ea[4] = {ev.x, ev.y, ev.z, ev.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
+      ST4(&Vrow[(j16 + j4) ^ sx], vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
+    }
+    tc_st_split16(t0 + E_A_HI + j16, t0 + E_A_LO + j16, vbar);
+  }
+  tc_role_sync(c);
+  if (c.issuer) {
+    tc_fence_after();
+    const uint32_t d = c.tbase + TC_E_BASE;
+    const uint32_t be = c.wts_saddr + (uint32_t)offsetof(Wts, BET);
+#pragma unroll
+    for (uint32_t ks = 0; ks < 4; ks++)
+      tc_mma3(d + E_D, d + E_A_HI + 8 * ks, d + E_A_LO + 8 * ks, be + ks * 32 * 32, be + 4 * NE * NE + ks * 32 * 32, 32,
+              tc_idesc(32), ks == 0);
+    tc_commit(c.mbar);
+  }
+  __syncwarp();
+  // ---- while the tensor core runs: dWE2[j][k] += sum_p V[p][j] * E1[p][k] (mma.sync, 3xTF32) ----
+  {
+    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ks++) {
+      const float* Va = Vs + (ks * 8 + t) * ROWE;
+      const float* Vb = Va + 4 * ROWE;
+      const float* Ea = E1s + (ks * 8 + t) * ROWE;
+      const float* Eb = Ea + 4 * ROWE;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        split_tf32(Va[(mt * 16 + g) ^ tx], ah[mt][0], al[mt][0]);
+        split_tf32(Va[(mt * 16 + g + 8) ^ tx], ah[mt][1], al[mt][1]);
+        split_tf32(Vb[(mt * 16 + g) ^ tx], ah[mt][2], al[mt][2]);
+        split_tf32(Vb[(mt * 16 + g + 8) ^ tx], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Ea[(nt * 8 + g) ^ tx], bh0, bl0);
+        split_tf32(Eb[(nt * 8 + g) ^ tx], bh1, bl1);
+        mma_3xtf32(acc.c[0][nt], ah[0], al[0], bh0, bh1, bl0, bl1);
+        mma_3xtf32(acc.c[1][nt], ah[1], al[1], bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  acc.s1 += colsum<ROWE>(Vs, lane);  // dbE2
+  __syncwarp();                      // Vs rows may now be overwritten
+  // ---- e1bar = WE2^T vbar is in TMEM: layer-1 reverse sweep; ubar_k -> Vs row ----
+  tc_wait_mma(c);
+#pragma unroll
+  for (int k16 = 0; k16 < NE; k16 += 16) {
+    float eb[16];
+    tc_ld16(t0 + E_D + k16, eb);
+    tc_wait_ld();
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const float4 ev = LD4(&E1row[(k16 + k4) ^ sx]);
+      const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
+      float ub[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) ub[i] = eb[k4 + i] * fmaf(-ea[i], ea[i], ea[i]);
+      ST4(&Vrow[(k16 + k4) ^ sx], ub[0], ub[1], ub[2], ub[3]);
+    }
+  }
+  // ---- gate reverse sweep + dbE -> E1s row (free now) ----
+  {
+    float ch[32];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const float s = sigm(fmaf(R, w.WgL[i], w.bgL[i]));
+      const float ub = gate_grads ? gbar * w.wg[i] * fmaf(-s, s, s) : 0.0f;
+      ch[i] = ub * R;
+      ch[10 + i] = ub;
+      ch[20 + i] = gate_grads ? gbar * s : 0.0f;
+    }
+    ch[30] = gate_grads ? gbar : 0.0f;
+    ch[31] = Ebar;
+#pragma unroll
+    for (int c4 = 0; c4 < 32; c4 += 4) ST4(&E1row[c4 ^ sx], ch[c4], ch[c4 + 1], ch[c4 + 2], ch[c4 + 3]);
+  }
+  __syncwarp();
+  {
+    float plain, weighted;
+    colsum_w<ROWE>(Vs, lane, R, plain, weighted);
+    acc.s2 += weighted;  // dWE1[k] = sum_p ubar_k R_p
+    acc.s3 += plain;     // dbE1
+  }
+  acc.s4 += colsum<ROWE>(E1s, lane);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel.  NEV = MLP evaluations per point (2: poc, 1: train.py); TRAIN = with reverse sweep
+//   warp = role * 4 + group;  role < NEV: MLP evaluation, role == NEV: E-net + gate
+// ---------------------------------------------------------------------------------------------
+template <int NEV, bool TRAIN>
+__global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const StepParams p) {
+  constexpr int G = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Wts& w = *reinterpret_cast<Wts*>(smem_raw);  // only the first WTS_TC_BYTES are staged / valid
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw + WTS_TC_BYTES);  // [0]: weight copy, [1..3]: roles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + WTS_TC_BYTES + 32);
+  float2* mbox = reinterpret_cast<float2*>(smem_raw + WTS_TC_BYTES + 64);
+  float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int role = warp >> 2, grp = warp & 3;
+  const bool is_mlp = role < NEV;
+  const int sx = swz(lane);
+
+  // ---- one-time setup: TMEM allocation (warp 0), mbarriers, weight image by TMA bulk copy ----
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 32) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbars[0])),
+                 "r"((uint32_t)WTS_TC_BYTES)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&w)),
+        "l"(p.wts), "r"((uint32_t)WTS_TC_BYTES), "r"(smem_u32(&mbars[0]))
+        : "memory");
+  }
+  mbar_wait(smem_u32(&mbars[0]), 0);
+
+  TcCtx c;
+  c.tbase = *tmem_slot;
+  c.tlane = c.tbase + ((uint32_t)(grp * 32) << 16);
+  c.mbar = smem_u32(&mbars[1 + role]);
+  c.phase = 0;
+  c.bar_id = 5 + role;
+  c.issuer = (grp == 0) && (lane == 0);
+  c.wts_saddr = smem_u32(&w);
+  const uint32_t cb = is_mlp ? (uint32_t)role * TC_MLP_COLS : TC_E_BASE;
+
+  float* gstash = stash + grp * tc_group_stash_floats<NEV>();
+  float* Hs = gstash + (is_mlp ? role * EVAL_STASH : NEV * EVAL_STASH);
+  float* Gs = Hs + (is_mlp ? 32 * ROWH : 32 * ROWE);  // for the E-net warp: Hs = E1s, Gs = Vs
+  float2* gbox = mbox + grp * (2 * 3 * 32);
+
+  double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
+  if (TRAIN) { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
+  const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
+  const float sN = p.vc.sN, cL = p.vc.cL, cV = p.vc.cV, cE = p.vc.cE;
+
+  TcAcc acc;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) acc.c[a][b][cc] = 0.0f;
+  acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = 0.0f;
+
+  // every warp of the CTA walks the same super-tiles (the role barriers need all 4 groups); groups whose
+  // 32 points lie beyond n compute on a clamped index with zero weight
+  const long long nsuper = (p.n + 127) >> 7;
+  int it = 0;
+  for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
+    const long long pidx = st * 128 + grp * 32 + lane;
+    const bool valid = pidx < p.n;
+    const long long pi = valid ? pidx : (p.n - 1);
+    const Geom g = load_geom(p, pi);
+    float2* box = gbox + (it & 1) * (3 * 32);
+
+    // the evaluation at the inversion image swaps the roles of the two nuclei (poc/main.py:255-256)
+    const bool sw = (role == 1) && is_mlp;
+    const float a = sw ? g.f2 : g.f1, b = sw ? g.f1 : g.f2;
+    const float al1 = sw ? g.al2 : g.al1, al2 = sw ? g.al1 : g.al2;
+    const float al11 = sw ? g.al22 : g.al11, al22 = sw ? g.al11 : g.al22;
+    const float al12 = g.al12;
+
+    if (is_mlp) {
+      float Nv, Dv;
+      tc_mlp_forward<TRAIN>(w, c, cb, a, b, al1, al2, al11, al12, al22, Hs + lane * ROWH, Gs + lane * ROWH, sx, Nv, Dv);
+      box[role * 32 + lane] = make_float2(Nv, Dv);
+    } else {
+      const float E = tc_enet_forward<TRAIN>(w, c, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx);
+      const float gt = tc_gate_forward(w, g.R);
+      box[2 * 32 + lane] = make_float2(E, gt);
+    }
+    named_barrier(1 + grp, (NEV + 1) * 32);
+
+    // ---- combine (every role recomputes the few scalars it needs) ----
+    float2 m0 = box[lane];
+    if (NEV == 2) { const float2 m1 = box[32 + lane]; m0.x += m1.x; m0.y += m1.y; }
+    const float2 me = box[2 * 32 + lane];
+    const float E = me.x, gate = me.y;
+    const float N = fmaf(sN, m0.x, w.bo), DN = sN * m0.y;
+    const float q = g.ir1 + g.ir2;
+    const float fs = g.f1 + g.f2;
+    const float psi = fmaf(gate, N, fs);
+    const float lcao = fmaf(cL, fs, fmaf(cV - 2.0f * cL, fmaf(g.f1, g.ir1, g.f2 * g.ir2),
+                                          cV * fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+    const float inner = fmaf(cL, DN, cV * q * N);
+    const float res = fmaf(gate, inner, fmaf(cE * E, psi, lcao));
+
+    if (!TRAIN) {
+      if (valid) {
+        if (role == 0) {
+          if (p.psi) p.psi[pidx] = psi;
+          if (p.lap) p.lap[pidx] = g.al1 + g.al2 + gate * DN;
+          if (p.res) p.res[pidx] = res;
+          if (p.hpsi)
+            p.hpsi[pidx] = fmaf(gate, fmaf(-0.5f, DN, -q * N),
+                                fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+        } else if (!is_mlp) {
+          if (p.E_out) p.E_out[pidx] = E;
+        }
+      }
+      continue;
+    }
+
+    // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
+    float m1f, m2f;
+    if (p.mask) {
+      const unsigned mk = p.mask[pi];
+      m1f = (mk & 1u) ? 1.0f : 0.0f;
+      m2f = (mk & 2u) ? 1.0f : 0.0f;
+    } else {
+      m1f = (g.ir1 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+      m2f = (g.ir2 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+    }
+    const float vw = valid ? 1.0f : 0.0f;
+    const float rbar = 2.0f * w_pde * res * vw;
+    const float pbar = 2.0f * fmaf(w_bc1, m1f, w_bc2 * m2f) * psi * vw;
+    if (is_mlp) {
+      const float lamN = fmaf(rbar, gate * fmaf(cV, q, cE * E), pbar * gate);
+      const float lamD = rbar * cL * gate;
+      float extra[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) extra[i] = 0.0f;
+      if (role == 0) {
+        extra[0] = res * res * vw;
+        extra[1] = psi * psi * m1f * vw;
+        extra[2] = psi * psi * m2f * vw;
+        extra[3] = E * vw;
+        extra[4] = p.base_grads ? lamN : 0.0f;  // dL/dbo
+        extra[5] = m1f * vw;
+        extra[6] = m2f * vw;
+      }
+      if (p.base_grads) {
+        tc_mlp_backward(w, c, cb, a, b, al1, al2, al11, al12, al22, sN * lamN, sN * lamD, Hs, Gs, lane, extra, acc);
+      } else if (role == 0) {
+        tc_mlp_extras_only(Hs, lane, extra, acc);
+      }
+    } else {
+      if (valid && p.E_out) p.E_out[pidx] = E;
+      const float gbar = fmaf(rbar, fmaf(cE * E, N, inner), pbar * N);
+      const float Ebar = rbar * cE * psi;
+      tc_enet_backward(w, c, g.R, Ebar, gbar, p.gate_grads != 0, Hs, Gs, lane, acc);
+    }
+  }
+
+  // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(c.tbase) : "memory");
+  }
+  if (!TRAIN) return;
+
+  // ---- fold: every warp writes its accumulators into its own row of floats (the stash is free now), then all
+  //      threads add the rows entry by entry in a fixed order, in double -> one deterministic row per CTA ----
+  {
+    float* myrow = stash + warp * NPART;
+    for (int i = lane; i < NPART; i += 32) myrow[i] = 0.0f;
+    __syncwarp();
+    const int gq = lane >> 2, tq = lane & 3;
+    if (is_mlp) {
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0];
+        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1];
+        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2];
+        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3];
+      }
+      myrow[lane < 16 ? O_B2 + lane : O_WO + lane - 16] = acc.s0;
+      myrow[lane < 16 ? O_W1 + 2 * lane : O_W1 + 2 * (lane - 16) + 1] = acc.s1;
+      if (lane < 16) myrow[O_B1 + lane] = acc.s2;
+      else if (role == 0) {
+        const int e = lane - 16;
+        const int dst = e == 0 ? S_RES2 : e == 1 ? S_PSI1 : e == 2 ? S_PSI2 : e == 3 ? S_E
+                      : e == 4 ? O_BO : e == 5 ? S_CNT1 : e == 6 ? S_CNT2 : -1;
+        if (dst >= 0) myrow[dst] = acc.s2;
+      }
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const int j = mt * 16 + gq, k = nt * 8 + 2 * tq;
+          myrow[O_WE2 + j * NE + k] = acc.c[mt][nt][0];
+          myrow[O_WE2 + j * NE + k + 1] = acc.c[mt][nt][1];
+          myrow[O_WE2 + (j + 8) * NE + k] = acc.c[mt][nt][2];
+          myrow[O_WE2 + (j + 8) * NE + k + 1] = acc.c[mt][nt][3];
+        }
+      myrow[O_WE + lane] = acc.s0;
+      myrow[O_BE2 + lane] = acc.s1;
+      myrow[O_WE1 + lane] = acc.s2;
+      myrow[O_BE1 + lane] = acc.s3;
+      const int dst = lane < 10 ? O_WGL + lane : lane < 20 ? O_BGL + lane - 10 : lane < 30 ? O_WG + lane - 20
+                    : lane == 30 ? O_BG : O_BE;
+      myrow[dst] = acc.s4;
+    }
+  }
+  __syncthreads();
+  constexpr int nwarps = (NEV + 1) * G;
+  double* row = p.partials + (size_t)blockIdx.x * NPART;
+  for (int i = tid; i < NPART; i += blockDim.x) {
+    double sum = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < nwarps; wv++) sum += (double)stash[wv * NPART + i];
+    row[i] = sum;
+  }
+}
+
+// =================================================================================================
+// host-side launcher
+// =================================================================================================
+template <int NEV, bool TRAIN>
+static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t st) {
+  auto kern = pinn_step_tc_kernel<NEV, TRAIN>;
+  constexpr size_t smem = tc_smem_bytes<NEV>();
+  static bool configured[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  kern<<<grid, (NEV + 1) * 128, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
+  if (nev == 2) return train ? launch_step_tc_t<2, true>(p, grid, st) : launch_step_tc_t<2, false>(p, grid, st);
+  return train ? launch_step_tc_t<1, true>(p, grid, st) : launch_step_tc_t<1, false>(p, grid, st);
+}
+
+}  // namespace pinn
