@@ -101,39 +101,59 @@ struct Geom {
   float R;
 };
 
-__device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) {
+// raw coordinates of one point, already relative to the two nuclei (5 registers; lets a kernel prefetch the next tile)
+struct RawPt {
   float dx1, dx2, y, z, R;
+};
+__device__ __forceinline__ RawPt load_raw(const StepParams& p, long long i) {
+  RawPt r;
   if (p.in_f64) {
     const double xd = ((const double*)p.x)[i], Rd = ((const double*)p.R)[i];
-    dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
-    dx2 = (float)(xd + Rd);
-    y = (float)((const double*)p.y)[i];
-    z = (float)((const double*)p.z)[i];
-    R = (float)Rd;
+    r.dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
+    r.dx2 = (float)(xd + Rd);
+    r.y = (float)((const double*)p.y)[i];
+    r.z = (float)((const double*)p.z)[i];
+    r.R = (float)Rd;
   } else {
     const float xf = ((const float*)p.x)[i];
-    R = ((const float*)p.R)[i];
-    dx1 = xf - R;
-    dx2 = xf + R;
-    y = ((const float*)p.y)[i];
-    z = ((const float*)p.z)[i];
+    r.R = ((const float*)p.R)[i];
+    r.dx1 = xf - r.R;
+    r.dx2 = xf + r.R;
+    r.y = ((const float*)p.y)[i];
+    r.z = ((const float*)p.z)[i];
   }
+  return r;
+}
+__device__ __forceinline__ Geom geom_from_raw(const RawPt& r) {
   Geom g;
-  const float yz = fmaf(y, y, z * z);
-  const float q1 = fmaf(dx1, dx1, yz), q2 = fmaf(dx2, dx2, yz);
+  const float yz = fmaf(r.y, r.y, r.z * r.z);
+  const float q1 = fmaf(r.dx1, r.dx1, yz), q2 = fmaf(r.dx2, r.dx2, yz);
   g.ir1 = rsqrtf(q1);
   g.ir2 = rsqrtf(q2);
   const float r1 = q1 * g.ir1, r2 = q2 * g.ir2;
   g.f1 = __expf(-r1);
   g.f2 = __expf(-r2);
-  const float c12 = fmaf(dx1, dx2, yz) * g.ir1 * g.ir2;
+  const float c12 = fmaf(r.dx1, r.dx2, yz) * g.ir1 * g.ir2;
   g.al1 = g.f1 * fmaf(-2.0f, g.ir1, 1.0f);
   g.al2 = g.f2 * fmaf(-2.0f, g.ir2, 1.0f);
   g.al11 = g.f1 * g.f1;
   g.al22 = g.f2 * g.f2;
   g.al12 = 2.0f * g.f1 * g.f2 * c12;
-  g.R = R;
+  g.R = r.R;
   return g;
+}
+__device__ __forceinline__ Geom load_geom(const StepParams& p, long long i) { return geom_from_raw(load_raw(p, i)); }
+
+// N sigmoids stage by stage (all EX2, then all RCP) so that the MUFU latencies overlap inside one warp
+template <int N>
+__device__ __forceinline__ void sigm_n(const float (&u)[N], float (&s)[N]) {
+  float e[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(u[i] * -1.4426950408889634f));
+#pragma unroll
+  for (int i = 0; i < N; i++) e[i] = 1.0f + e[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) s[i] = rcp_approx(e[i]);
 }
 
 #define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))

@@ -681,11 +681,20 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   // 32 points lie beyond n compute on a clamped index with zero weight
   const long long nsuper = (p.n + 127) >> 7;
   int it = 0;
+  RawPt nxt;
+  {
+    const long long i0 = (long long)blockIdx.x * 128 + grp * 32 + lane;
+    nxt = load_raw(p, i0 < p.n ? i0 : p.n - 1);
+  }
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
     const long long pidx = st * 128 + grp * 32 + lane;
     const bool valid = pidx < p.n;
     const long long pi = valid ? pidx : (p.n - 1);
-    const Geom g = load_geom(p, pi);
+    const Geom g = geom_from_raw(nxt);
+    {  // coordinates of the next super-tile: issued now, consumed one iteration later
+      const long long in = pidx + (long long)gridDim.x * 128;
+      nxt = load_raw(p, in < p.n ? in : p.n - 1);
+    }
     float2* box = gbox + (it & 1) * (3 * 32);
 
     // the evaluation at the inversion image swaps the roles of the two nuclei (poc/main.py:255-256)
