@@ -63,12 +63,14 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4
 // Column sum over the 32 rows (points) of a swizzled stash: lane sums column `col`.
 template <int ROW>
 __device__ __forceinline__ float colsum(const float* __restrict__ base, int col) {
+  // four row-phase pointers (the swizzle depends on row & 3 only); fully unrolled so that every load is
+  // [pointer + immediate] and no per-row address arithmetic is left
   const float* p0 = base + col;
   const float* p1 = base + ROW + (col ^ 8);
   const float* p2 = base + 2 * ROW + (col ^ 16);
   const float* p3 = base + 3 * ROW + (col ^ 24);
   float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll 2
+#pragma unroll
   for (int p = 0; p < 32; p += 4) {
     s0 += p0[p * ROW]; s1 += p1[p * ROW]; s2 += p2[p * ROW]; s3 += p3[p * ROW];
   }
@@ -77,11 +79,14 @@ __device__ __forceinline__ float colsum(const float* __restrict__ base, int col)
 // Weighted column sums: returns sum_p base[p][col] and sum_p wgt_p * base[p][col] (wgt = per-lane value of row p)
 template <int ROW>
 __device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col, float wgt, float& plain, float& weighted) {
+  const float* p0 = base + col;
+  const float* p1 = base + ROW + (col ^ 8);
+  const float* p2 = base + 2 * ROW + (col ^ 16);
+  const float* p3 = base + 3 * ROW + (col ^ 24);
   float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
-#pragma unroll 2
+#pragma unroll
   for (int p = 0; p < 32; p += 4) {
-    const float v0 = base[(p + 0) * ROW + col], v1 = base[(p + 1) * ROW + (col ^ 8)];
-    const float v2 = base[(p + 2) * ROW + (col ^ 16)], v3 = base[(p + 3) * ROW + (col ^ 24)];
+    const float v0 = p0[p * ROW], v1 = p1[p * ROW], v2 = p2[p * ROW], v3 = p3[p * ROW];
     s0 += v0; s1 += v1; s0 += v2; s1 += v3;
     t0 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 0), v0, t0);
     t1 = fmaf(__shfl_sync(0xffffffffu, wgt, p + 1), v1, t1);

@@ -32,7 +32,20 @@ namespace pinn {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.wait::ld that also "touches" the loaded registers: their consumers cannot be scheduled above the wait, and no
+// memory clobber is needed (shared-memory loads of weights may move freely around the TMEM traffic)
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tc_wait_ld(float (&v)[N]) {
+  static_assert(N == 8 || N == 16, "8 or 16 registers");
+  if constexpr (N == 8)
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+  else
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
+}
 
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -73,15 +86,13 @@ __device__ __forceinline__ void tc_mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
                "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-               : "memory");
+               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]));
 }
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
+               : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
@@ -91,8 +102,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
+      : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
@@ -230,7 +240,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
     tc_ld8(t0 + F_P + j8, P00);
     tc_ld8(t0 + F_P + NH + j8, P01);
     tc_ld8(t0 + F_P + 2 * NH + j8, P11);
-    tc_wait_ld();
+    tc_wait_ld(V0); tc_wait_ld(V1); tc_wait_ld(V2); tc_wait_ld(P00); tc_wait_ld(P01); tc_wait_ld(P11);
 #pragma unroll
     for (int j4 = 0; j4 < 8; j4 += 4) {
       const float4 b2v = LD4(&w.b2[j8 + j4]), wov = LD4(&w.wo[j8 + j4]);
@@ -378,7 +388,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
     tc_ld8(t0 + 1 * NH + k8, hb1);
     tc_ld8(t0 + 2 * NH + k8, hb2);
     tc_ld8(t0 + 3 * NH + k8, hb3);
-    tc_wait_ld();
+    tc_wait_ld(hb0); tc_wait_ld(hb1); tc_wait_ld(hb2); tc_wait_ld(hb3);
 #pragma unroll
     for (int k4 = 0; k4 < 8; k4 += 4) {
       const int kk = k8 + k4;
@@ -469,7 +479,7 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
   for (int j16 = 0; j16 < NE; j16 += 16) {
     float v[16];
     tc_ld16(t0 + E_D + j16, v);
-    tc_wait_ld();
+    tc_wait_ld(v);
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
       const float4 b2v = LD4(&w.bE2[j16 + j4]), wEv = LD4(&w.wE[j16 + j4]);
@@ -567,7 +577,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   for (int k16 = 0; k16 < NE; k16 += 16) {
     float eb[16];
     tc_ld16(t0 + E_D + k16, eb);
-    tc_wait_ld();
+    tc_wait_ld(eb);
 #pragma unroll
     for (int k4 = 0; k4 < 16; k4 += 4) {
       const float4 ev = LD4(&E1row[(k16 + k4) ^ sx]);
