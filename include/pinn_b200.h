@@ -136,6 +136,87 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n,
                            uint32_t grad_mask, float bcutoff,
                            double* sums_host, double* dtheta_host, float* E_out_host);
 
+/* =====================================================================================================
+ * Rows next to the hot path: device-side sampler, fused Adam, a device-resident trainer,
+ * the E(R)/gate curve and dense-grid quadrature.  Same conventions as above.
+ * ===================================================================================================== */
+
+/*
+ * Collocation sampler + clamp + boundary sets: replaces train.py:26-39 and sampling()/radial()/torch.where of
+ * poc/main.py:124-156, 390-393 for runs that do not need the host's torch RNG stream.
+ * Point i of batch `batch` is Philox4x32-10(counter = {i_lo, i_hi, batch_lo, batch_hi}, key = seed); word k of the
+ * output, u = (word >> 8) * 2^-24 in [0,1), gives x, y, z, R = lo + (hi - lo) * u with box = {xL,xR,yL,yR,zL,zR,RL,RR}.
+ * Then, literally as the reference: x = cutoff where r1 < cutoff or r2 < cutoff (radii of the unclamped point), sets
+ * r1 >= bcutoff / r2 >= bcutoff after the clamp (bit0 / bit1 of mask).  counts: device, 2 x uint64 set sizes;
+ * weights: device, 3 double {1/n, 1/count1, 1/count2}.  All outputs float32 / device.
+ */
+int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const float box[8], float cutoff, float bcutoff,
+                float* x, float* y, float* z, float* R, uint8_t* mask, uint64_t* counts, double* weights, void* stream);
+
+/*
+ * One optimizer step of torch.optim.Adam (no weight decay, no amsgrad) over the 1521 float64 parameters, fused with
+ * the reference loops' bookkeeping (train.py:58-72; poc/main.py:403-417).  All pointers are device memory.
+ *  theta, m, v   in/out float64 [1521];  grad: dLtot/dtheta;  sums: the 8 sums of pinn_loss_fwd_bwd
+ *  theta32       out float32 [1521]: the copy the next pinn_loss_fwd_bwd reads
+ *  step          in/out uint64: optimizer steps done (= tt of this step); incremented
+ *  best_mode 0   train.py: if tt == 0 or Ltot < best_loss, keep Ltot and the PRE-step parameters
+ *  best_mode 1   poc: if tt > best_after and Ltot < best_loss (initialise to 10), keep Ltot and the POST-step parameters
+ *  hist          NULL or [hist_cap][4] doubles: row tt = {Ltot, Lpde, Lbc, E}, E = mean over the batch
+ *                (history_mean_E, train.py:64) or E of the last point (poc/main.py:411)
+ *  grad_mask     tensors whose bit is clear are frozen: no update, state untouched
+ */
+int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const double* grad, const double* sums, float* theta32,
+                   uint64_t* step, double* best_loss, double* best_theta, int64_t* best_step, double* hist, int64_t hist_cap,
+                   int64_t n, double lr, double beta1, double beta2, double eps, uint32_t grad_mask, int best_mode,
+                   int64_t best_after, int history_mean_E, void* stream);
+
+/* Device-resident training loop: sampler -> fused loss/gradient -> Adam, one CUDA-graph replay per step, no host
+ * synchronisation until pinn_trainer_read.  Mirrors train() of train.py:21-72 and poc/main.py:359-430. */
+typedef struct pinn_train_config {
+  int variant;               /* PINN_VARIANT_* */
+  int best_mode;             /* 0 train.py, 1 poc (see pinn_adam_step) */
+  int history_mean_E;        /* history column 3: 1 mean E (train.py), 0 E of the last point (poc) */
+  int sc_sampling;           /* resample every sc_sampling steps (train.py:79; params['sc_sampling']) */
+  int64_t n;                 /* points per step */
+  int64_t freeze_after;      /* no resampling for tt >= freeze_after (poc: 0.9*epochs; train.py: never -> INT64_MAX) */
+  int64_t best_after;        /* poc: 0.5*epochs */
+  int64_t history_capacity;  /* rows of the device history */
+  uint64_t seed;
+  float xL, xR, yL, yR, zL, zR, RL, RR, cutoff, bcutoff;
+  uint32_t grad_mask;
+  double lr, beta1, beta2, eps;
+} pinn_train_config;
+typedef struct pinn_trainer pinn_trainer;
+int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const double* theta0_host, pinn_trainer** out);
+int pinn_trainer_destroy(pinn_trainer* t);
+int pinn_trainer_load_state(pinn_trainer* t, const double* theta, const double* m, const double* v, int64_t step);
+int pinn_trainer_set_batch(pinn_trainer* t, const float* x, const float* y, const float* z, const float* R, const uint8_t* mask,
+                           const double* weights_host);
+int pinn_trainer_run(pinn_trainer* t, int64_t steps, int resample, int use_graph);
+int pinn_trainer_read(pinn_trainer* t, double* theta, double* m, double* v, double* best_theta, double* scalars, double* history,
+                      int64_t history_rows);
+int pinn_trainer_batch(pinn_trainer* t, float** x, float** y, float** z, float** R, uint8_t** mask);
+void* pinn_trainer_stream(pinn_trainer* t);
+
+/*
+ * E(R) of the E-net with its first and second derivative (autograd in poc/main.py:1324-1332) and the gate g(R)
+ * (returnGate, poc/main.py:164-176; energy.py:26-31 evaluates the same E-net).  theta: device float32 [1521];
+ * R: device float64 [n]; outputs device float64 [n], any may be NULL.
+ */
+int pinn_enet_curve(pinn_handle* h, const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
+                    void* stream);
+
+/*
+ * Dense-grid quadrature at one R: replaces the grid evaluation + integra3d of energy_from_psi,
+ * energy_from_psi_LCAO and dEdR_int (poc/main.py:438-494, 646-676, 179-186) without materialising the grid.
+ * Grid = meshgrid('ij') of linspace(lim[0],lim[1],nx) x linspace(lim[2],lim[3],ny) x linspace(lim[4],lim[5],nz);
+ * wx, wy, wz: device float64 1-D quadrature weights (Simpson; the product rule equals the nested simps calls).
+ * out (device, 8 double): {sum w psi H psi, sum w psi^2, sum w lcao H lcao, sum w lcao^2, sum w dV/dR psi^2, E_net(R), 0, 0}
+ * so that E_int = out[0]/out[1], E_lcao = out[2]/out[3], dE/dR|HF = out[4]/out[1] - 1/(2 R^2).
+ */
+int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, int ny, int nz, const double lim[6], double R,
+                     const double* wx, const double* wy, const double* wz, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,9 @@ call sites:
 * ``fields``          - fused ``parametricPsi`` + ``hamiltonian`` (poc/main.py:321, 118)
 * ``patch_nn_ion``    - monkey-patches an ``NN_ion`` class so the reference training loop runs unchanged
 * ``run_train_py``    - runs the reference ``train.py`` with lines 41-57 routed through the kernel
+* ``trainer``         - device-resident loop: Philox sampler, fused Adam, CUDA-graph replay (train.py:21-72; poc/main.py:359-430)
+* ``analysis``        - dense-grid energies / Hellmann-Feynman force / E(R) curve (poc/main.py:438-517, 639-676; energy.py)
+* ``convert``         - ``model.bin`` and ``.pt`` containers <-> packed parameters
 
 There is no CPU fallback: importing works anywhere, but every compute entry raises if the
 CUDA library or a B200 is missing.
@@ -20,10 +23,13 @@ from ._lib import lib, Handle, PinnError, library_path
 from .ops import (PinnLossPoc, PinnLossTrainPy, loss_poc, loss_trainpy, fields, loss_and_grad_raw,
                   indices_to_mask)
 from .patch import patch_nn_ion, run_train_py, trainpy_patched_source
+from . import analysis, convert, trainer
+from .trainer import Trainer, AdamState, adam_step, sample, train_trainpy, train_poc, init_trainpy
 
 __all__ = [
     "N_THETA", "POC_TENSOR_NAMES", "TRAINPY_TENSOR_NAMES", "pack_poc", "unpack_poc", "pack_trainpy",
     "unpack_trainpy", "FINE_TUNE_GRAD_MASK", "lib", "Handle", "PinnError", "library_path", "PinnLossPoc",
     "PinnLossTrainPy", "loss_poc", "loss_trainpy", "fields", "loss_and_grad_raw", "indices_to_mask",
-    "patch_nn_ion", "run_train_py", "trainpy_patched_source",
+    "patch_nn_ion", "run_train_py", "trainpy_patched_source", "analysis", "convert", "trainer", "Trainer", "AdamState",
+    "adam_step", "sample", "train_trainpy", "train_poc", "init_trainpy",
 ]

@@ -10,7 +10,21 @@ _LIB_NAME = "libpinn_b200.so"
 EXPORTS = [
     "pinn_version", "pinn_theta_size", "pinn_theta_offsets", "pinn_create", "pinn_destroy", "pinn_last_error",
     "pinn_launch_count", "pinn_set_engine", "pinn_get_engine", "pinn_profile_begin", "pinn_profile_collect", "pinn_loss_fwd_bwd", "pinn_fields", "pinn_loss_fwd_bwd_host",
+    "pinn_sample", "pinn_adam_step", "pinn_enet_curve", "pinn_grid_reduce", "pinn_trainer_create", "pinn_trainer_destroy",
+    "pinn_trainer_load_state", "pinn_trainer_set_batch", "pinn_trainer_run", "pinn_trainer_read", "pinn_trainer_batch",
+    "pinn_trainer_stream",
 ]
+
+
+class TrainConfig(ctypes.Structure):
+    """pinn_train_config of include/pinn_b200.h"""
+    _fields_ = [("variant", ctypes.c_int), ("best_mode", ctypes.c_int), ("history_mean_E", ctypes.c_int),
+                ("sc_sampling", ctypes.c_int), ("n", ctypes.c_int64), ("freeze_after", ctypes.c_int64),
+                ("best_after", ctypes.c_int64), ("history_capacity", ctypes.c_int64), ("seed", ctypes.c_uint64),
+                ("xL", ctypes.c_float), ("xR", ctypes.c_float), ("yL", ctypes.c_float), ("yR", ctypes.c_float),
+                ("zL", ctypes.c_float), ("zR", ctypes.c_float), ("RL", ctypes.c_float), ("RR", ctypes.c_float),
+                ("cutoff", ctypes.c_float), ("bcutoff", ctypes.c_float), ("grad_mask", ctypes.c_uint32),
+                ("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double)]
 
 
 class PinnError(RuntimeError):
@@ -63,6 +77,33 @@ def lib():
         L.pinn_fields.restype = i32
         L.pinn_loss_fwd_bwd_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, u32, f32, vp, vp, vp]
         L.pinn_loss_fwd_bwd_host.restype = i32
+        u64, f64 = ctypes.c_uint64, ctypes.c_double
+        L.pinn_sample.argtypes = [vp, i64, u64, u64, ctypes.POINTER(f32), f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.pinn_sample.restype = i32
+        L.pinn_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, f64, f64, f64, f64, u32,
+                                     i32, i64, i32, vp]
+        L.pinn_adam_step.restype = i32
+        L.pinn_enet_curve.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+        L.pinn_enet_curve.restype = i32
+        L.pinn_grid_reduce.argtypes = [vp, i32, vp, i32, i32, i32, ctypes.POINTER(f64), f64, vp, vp, vp, vp, vp]
+        L.pinn_grid_reduce.restype = i32
+        L.pinn_trainer_create.argtypes = [vp, ctypes.POINTER(TrainConfig), vp, ctypes.POINTER(vp)]
+        L.pinn_trainer_create.restype = i32
+        L.pinn_trainer_destroy.argtypes = [vp]
+        L.pinn_trainer_destroy.restype = i32
+        L.pinn_trainer_load_state.argtypes = [vp, vp, vp, vp, i64]
+        L.pinn_trainer_load_state.restype = i32
+        L.pinn_trainer_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.pinn_trainer_set_batch.restype = i32
+        L.pinn_trainer_run.argtypes = [vp, i64, i32, i32]
+        L.pinn_trainer_run.restype = i32
+        L.pinn_trainer_read.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64]
+        L.pinn_trainer_read.restype = i32
+        L.pinn_trainer_batch.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                         ctypes.POINTER(vp), ctypes.POINTER(vp)]
+        L.pinn_trainer_batch.restype = i32
+        L.pinn_trainer_stream.argtypes = [vp]
+        L.pinn_trainer_stream.restype = vp
         _lib = L
         return L
 

@@ -6,57 +6,9 @@
 #include <string>
 #include <vector>
 
-#include "../../include/pinn_b200.h"
-#include "pinn_common.cuh"
+#include "pinn_handle.h"
 
-#include "pinn_launch.h"
-
-using namespace pinn;
-
-struct pinn_handle {
-  int device = 0;
-  int sm_count = 0;
-  Wts* wts = nullptr;              // prepared weight image
-  float* theta_dev = nullptr;      // staging for the *_host entry (1536 float)
-  double* weights_dev = nullptr;   // 3 double
-  unsigned long long* counts = nullptr;
-  double* partials = nullptr;      // [max_rows][NPART]
-  int max_rows = 0;
-  // *_host entry
-  void* stage_dev = nullptr;       // coordinates + mask
-  size_t stage_bytes = 0;
-  double* out_dev = nullptr;       // 8 sums + 1521 grads
-  double* out_pinned = nullptr;
-  float* theta_pinned = nullptr;
-  double* weights_pinned = nullptr;
-  cudaStream_t s_copy = nullptr, s_main = nullptr;
-  cudaEvent_t ev_copy = nullptr;
-  int64_t launches = 0;
-  int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
-  bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
-  std::vector<cudaEvent_t> ev_pool;
-  size_t ev_used = 0;
-  std::string err;
-  std::mutex mu;
-};
-
-static std::string g_create_err;
-
-static int fail(pinn_handle* h, int code, const char* what) {
-  char buf[512];
-  if (code > 0)
-    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString((cudaError_t)code),
-             cudaGetErrorName((cudaError_t)code));
-  else
-    snprintf(buf, sizeof(buf), "%s", what);
-  if (h) h->err = buf; else g_create_err = buf;
-  return code;
-}
-#define CU(h, call)                                   \
-  do {                                                \
-    cudaError_t e__ = (call);                         \
-    if (e__ != cudaSuccess) return fail(h, (int)e__, #call); \
-  } while (0)
+std::string g_create_err;
 
 static const int kOffsets[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
                                  O_WGL, O_BGL, O_WG, O_BG, NTHETA};
@@ -93,6 +45,8 @@ int pinn_create(int device, pinn_handle** out) {
   CU(h, cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
   CU(h, cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
   CU(h, cudaMalloc(&h->out_dev, NPART * sizeof(double)));
+  CU(h, cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
+  CU(h, cudaMalloc(&h->batch_counter, sizeof(unsigned long long)));
   CU(h, cudaMallocHost(&h->out_pinned, NPART * sizeof(double)));
   CU(h, cudaMallocHost(&h->theta_pinned, NPART * sizeof(float)));
   CU(h, cudaMallocHost(&h->weights_pinned, 4 * sizeof(double)));
@@ -107,7 +61,7 @@ int pinn_destroy(pinn_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->weights_dev); cudaFree(h->counts);
-  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->out_dev);
+  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->out_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
   cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned); cudaFreeHost(h->weights_pinned);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_main) cudaStreamDestroy(h->s_main);

@@ -1,0 +1,60 @@
+// Private to the library: the handle behind the C ABI (include/pinn_b200.h) and the error helpers.
+#pragma once
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pinn_b200.h"
+#include "pinn_common.cuh"
+#include "pinn_launch.h"
+
+using namespace pinn;
+
+struct pinn_handle {
+  int device = 0;
+  int sm_count = 0;
+  Wts* wts = nullptr;              // prepared weight image
+  float* theta_dev = nullptr;      // staging for the *_host entry (1536 float)
+  double* weights_dev = nullptr;   // 3 double
+  unsigned long long* counts = nullptr;
+  double* partials = nullptr;      // [max_rows][NPART]
+  int max_rows = 0;
+  double* grid_partials = nullptr;  // [sm_count + 1][8] dense-grid quadrature rows
+  unsigned long long* batch_counter = nullptr;  // device counter used by the stand-alone pinn_sample entry
+  // *_host entry
+  void* stage_dev = nullptr;       // coordinates + mask
+  size_t stage_bytes = 0;
+  double* out_dev = nullptr;       // 8 sums + 1521 grads
+  double* out_pinned = nullptr;
+  float* theta_pinned = nullptr;
+  double* weights_pinned = nullptr;
+  cudaStream_t s_copy = nullptr, s_main = nullptr;
+  cudaEvent_t ev_copy = nullptr;
+  int64_t launches = 0;
+  int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
+  bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::string err;
+  std::mutex mu;
+};
+
+extern std::string g_create_err;
+
+inline int fail(pinn_handle* h, int code, const char* what) {
+  char buf[512];
+  if (code > 0)
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString((cudaError_t)code),
+             cudaGetErrorName((cudaError_t)code));
+  else
+    snprintf(buf, sizeof(buf), "%s", what);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+#define CU(h, call)                                   \
+  do {                                                \
+    cudaError_t e__ = (call);                         \
+    if (e__ != cudaSuccess) return fail(h, (int)e__, #call); \
+  } while (0)
+

@@ -7,6 +7,18 @@
 
 namespace pinn {
 
+// Dense-grid mode of the inference kernel (poc/main.py:438-517, 639-676): point p of the n = nx*ny*nz
+// grid is (i,j,k) = meshgrid 'ij' order of three linspaces, R is one value, and instead of per-point stores the kernel
+// accumulates the quadrature sums  S = sum_p w_p * {psi H psi, psi^2, lcao H lcao, lcao^2, (dV/dR) psi^2}.
+struct GridDesc {
+  int on;
+  int nx, ny, nz;
+  double x0, dx, y0, dy, z0, dz;  // linspace start / step
+  double R;
+  const double *wx, *wy, *wz;     // 1-D quadrature weights (Simpson), device
+  double* partials;               // [gridDim.x][8]
+};
+
 struct StepParams {
   const void *x, *y, *z, *R;
   const uint8_t* mask;
@@ -20,12 +32,14 @@ struct StepParams {
   float bcut;
   VariantCoef vc;
   int base_grads, gate_grads;  // reverse sweeps wanted (fine-tune mode clears both)
+  GridDesc grid;
 };
 
 cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
 int step_groups();
 // tcgen05 engine (pinn_step_tc.cu): super-tiles of 128 points, one persistent CTA per SM
 cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
+cudaError_t launch_grid_finish(const double* partials, int nrows, double* out, cudaStream_t st);
 cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st);
 cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st);
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,

@@ -615,6 +615,28 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   __syncwarp();
 }
 
+// coordinates of point `i`: from the caller's arrays, or generated from the grid descriptor (meshgrid 'ij' order;
+// positions are formed in double like the reference's linspace and rounded once, the nucleus offsets before rounding)
+__device__ __forceinline__ void grid_ijk(const GridDesc& g, long long i, int& ix, int& iy, int& iz) {
+  iz = (int)(i % g.nz);
+  const long long r = i / g.nz;
+  iy = (int)(r % g.ny);
+  ix = (int)(r / g.ny);
+}
+__device__ __forceinline__ RawPt tc_load_point(const StepParams& p, long long i) {
+  if (!p.grid.on) return load_raw(p, i);
+  int ix, iy, iz;
+  grid_ijk(p.grid, i, ix, iy, iz);
+  const double x = fma((double)ix, p.grid.dx, p.grid.x0);
+  RawPt r;
+  r.dx1 = (float)(x - p.grid.R);
+  r.dx2 = (float)(x + p.grid.R);
+  r.y = (float)fma((double)iy, p.grid.dy, p.grid.y0);
+  r.z = (float)fma((double)iz, p.grid.dz, p.grid.z0);
+  r.R = (float)p.grid.R;
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused kernel.  NEV = MLP evaluations per point (2: poc, 1: train.py); TRAIN = with reverse sweep
 //   warp = role * 4 + group;  role < NEV: MLP evaluation, role == NEV: E-net + gate
@@ -687,6 +709,8 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
       for (int cc = 0; cc < 4; cc++) acc.c[a][b][cc] = 0.0f;
   acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = 0.0f;
 
+  double gs0 = 0.0, gs1 = 0.0, gs2 = 0.0, gs3 = 0.0, gs4 = 0.0;  // dense-grid quadrature sums (role 0, inference only)
+
   // every warp of the CTA walks the same super-tiles (the role barriers need all 4 groups); groups whose
   // 32 points lie beyond n compute on a clamped index with zero weight
   const long long nsuper = (p.n + 127) >> 7;
@@ -694,16 +718,17 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   RawPt nxt;
   {
     const long long i0 = (long long)blockIdx.x * 128 + grp * 32 + lane;
-    nxt = load_raw(p, i0 < p.n ? i0 : p.n - 1);
+    nxt = tc_load_point(p, i0 < p.n ? i0 : p.n - 1);
   }
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
     const long long pidx = st * 128 + grp * 32 + lane;
     const bool valid = pidx < p.n;
     const long long pi = valid ? pidx : (p.n - 1);
     const Geom g = geom_from_raw(nxt);
+    const float cur_dx1 = nxt.dx1, cur_dx2 = nxt.dx2;
     {  // coordinates of the next super-tile: issued now, consumed one iteration later
       const long long in = pidx + (long long)gridDim.x * 128;
-      nxt = load_raw(p, in < p.n ? in : p.n - 1);
+      nxt = tc_load_point(p, in < p.n ? in : p.n - 1);
     }
     float2* box = gbox + (it & 1) * (3 * 32);
 
@@ -740,6 +765,26 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     const float res = fmaf(gate, inner, fmaf(cE * E, psi, lcao));
 
     if (!TRAIN) {
+      if (p.grid.on) {
+        if (valid && role == 0) {
+          int ix, iy, iz;
+          grid_ijk(p.grid, pidx, ix, iy, iz);
+          const double wq = p.grid.wx[ix] * p.grid.wy[iy] * p.grid.wz[iz];
+          // Hartree form of H psi (poc/main.py:118-120) with the cusp terms cancelled analytically, and its LCAO part
+          const float hl = fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1));
+          const float hpsi = fmaf(gate, fmaf(-0.5f, DN, -q * N), hl);
+          // dV/dR = -(x-R)/r1^3 + (x+R)/r2^3 (poc/main.py:637-642)
+          const float vr = fmaf(-cur_dx1, g.ir1 * g.ir1 * g.ir1, cur_dx2 * g.ir2 * g.ir2 * g.ir2);
+          gs0 += wq * (double)(psi * hpsi);
+          gs1 += wq * (double)(psi * psi);
+          gs2 += wq * (double)(fs * hl);
+          gs3 += wq * (double)(fs * fs);
+          gs4 += wq * (double)(vr * psi * psi);
+        } else if (!is_mlp && st == 0 && grp == 0 && lane == 0) {
+          p.grid.partials[8 * (size_t)gridDim.x] = (double)E;  // E(R) of the launch, behind the partial rows
+        }
+        continue;
+      }
       if (valid) {
         if (role == 0) {
           if (p.psi) p.psi[pidx] = psi;
@@ -803,7 +848,23 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(c.tbase) : "memory");
   }
-  if (!TRAIN) return;
+  if (!TRAIN) {
+    if (p.grid.on) {  // one row of quadrature sums per CTA, fixed order
+      double* red = reinterpret_cast<double*>(stash);
+      if (role == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gs1 += __shfl_xor_sync(0xffffffffu, gs1, o);
+          gs2 += __shfl_xor_sync(0xffffffffu, gs2, o); gs3 += __shfl_xor_sync(0xffffffffu, gs3, o);
+          gs4 += __shfl_xor_sync(0xffffffffu, gs4, o);
+        }
+        if (lane == 0) { red[grp * 8 + 0] = gs0; red[grp * 8 + 1] = gs1; red[grp * 8 + 2] = gs2; red[grp * 8 + 3] = gs3; red[grp * 8 + 4] = gs4; }
+      }
+      __syncthreads();
+      if (tid < 5) p.grid.partials[8 * (size_t)blockIdx.x + tid] = (red[tid] + red[8 + tid]) + (red[16 + tid] + red[24 + tid]);
+    }
+    return;
+  }
 
   // ---- fold: every warp writes its accumulators into its own row of floats (the stash is free now), then all
   //      threads add the rows entry by entry in a fixed order, in double -> one deterministic row per CTA ----
@@ -876,6 +937,24 @@ static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t 
     configured[dev] = true;
   }
   kern<<<grid, (NEV + 1) * 128, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// adds the per-CTA quadrature rows in a fixed order; out[5] = E(R) stored behind the rows
+__global__ void grid_finish_kernel(const double* __restrict__ partials, int nrows, double* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t < 5) {
+    double s = 0.0;
+    for (int r = 0; r < nrows; r++) s += partials[8 * (size_t)r + t];
+    out[t] = s;
+  } else if (t == 5) {
+    out[5] = partials[8 * (size_t)nrows];
+  } else if (t < 8) {
+    out[t] = 0.0;
+  }
+}
+cudaError_t launch_grid_finish(const double* partials, int nrows, double* out, cudaStream_t st) {
+  grid_finish_kernel<<<1, 32, 0, st>>>(partials, nrows, out);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,187 @@
+// Device-side pieces of the training loop around the fused step kernel:
+//   * collocation sampler + clamp + boundary sets (train.py:26-39; poc/main.py:124-156, 390-393), Philox4x32-10,
+//     one counter per point, so a batch never round-trips through the host;
+//   * fused Adam over the 1521 parameters in float64 with the reference's best-model bookkeeping
+//     (torch.optim.Adam semantics; train.py:58-60, 65-69; poc/main.py:403-417) and the per-step history;
+//   * E(R), dE/dR, d2E/dR2 and the gate along an R grid (energy.py:26-33; poc/main.py:164-176, 1324-1332).
+// Everything is launched on a caller-given stream and is CUDA-graph capturable (no host decisions inside a step).
+#include "pinn_device.cuh"
+#include "pinn_train.h"
+
+namespace pinn {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0,k1) -> 4 x 32 random bits
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }  // [0,1), 24 bits
+
+// One thread per point.  Point i of batch b uses counter (i_lo, i_hi, b_lo, b_hi) and key = seed; its four words give
+// x, y, z, R.  Clamp and sets follow the reference literally: both tests use the radii of the UN-clamped point
+// (train.py:32-35), the clamp writes the VALUE `cutoff` into x, and the sets are taken after it (train.py:36-39).
+__global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
+  const unsigned long long batch = *s.batch_counter;
+  unsigned c1 = 0, c2 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)batch, (uint32_t)(batch >> 32),
+                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32), r);
+    float x = fmaf(s.xR - s.xL, u01(r[0]), s.xL);
+    const float y = fmaf(s.yR - s.yL, u01(r[1]), s.yL);
+    const float z = fmaf(s.zR - s.zL, u01(r[2]), s.zL);
+    const float R = fmaf(s.RR - s.RL, u01(r[3]), s.RL);
+    const float yz = fmaf(y, y, z * z);
+    const float c2cut = s.cutoff * s.cutoff;
+    const bool near1 = fmaf(x - R, x - R, yz) < c2cut, near2 = fmaf(x + R, x + R, yz) < c2cut;
+    if (near1 || near2) x = s.cutoff;
+    const float b2 = s.bcutoff * s.bcutoff;
+    const unsigned m1 = fmaf(x - R, x - R, yz) >= b2, m2 = fmaf(x + R, x + R, yz) >= b2;
+    s.x[i] = x; s.y[i] = y; s.z[i] = z; s.R[i] = R;
+    s.mask[i] = (uint8_t)(m1 | (m2 << 1));
+    c1 += m1; c2 += m2;
+  }
+  c1 = __reduce_add_sync(0xffffffffu, c1);
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  __shared__ unsigned sh1[8], sh2[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh1[w] = c1; sh2[w] = c2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t1 = 0, t2 = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { t1 += sh1[k]; t2 += sh2[k]; }
+    atomicAdd(&s.counts[0], (unsigned long long)t1);  // integer atomics: order-independent result
+    atomicAdd(&s.counts[1], (unsigned long long)t2);
+  }
+}
+
+// weights {1/n, 1/|set1|, 1/|set2|} of the reference's means (empty set -> inf -> NaN loss, as in the reference),
+// and the batch counter moves on
+__global__ void sample_finish_kernel(const unsigned long long* counts, long long n, double* w, unsigned long long* batch_counter) {
+  w[0] = 1.0 / (double)n;
+  w[1] = 1.0 / (double)counts[0];
+  w[2] = 1.0 / (double)counts[1];
+  *batch_counter += 1ull;
+}
+
+cudaError_t launch_sample(const SampleParams& s, double* weights, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(s.counts, 0, 2 * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  long long blocks = (s.n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sample_kernel<<<(int)blocks, 256, 0, st>>>(s);
+  sample_finish_kernel<<<1, 1, 0, st>>>(s.counts, s.n, weights, s.batch_counter);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam: lerp first moment, bias corrections, eps outside the square root; no weight decay, no amsgrad)
+// in float64, the reference's parameter dtype, plus best-model bookkeeping and history
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) adam_kernel(const AdamParams a) {
+  __shared__ int take_best;
+  const unsigned long long t = *a.step;  // optimizer steps done so far = index tt of this step in the reference loops
+  const double Ltot = a.sums[0];
+  if (threadIdx.x == 0) {
+    bool tb;
+    if (a.best_mode == 0) tb = (t == 0ull) || (Ltot < *a.best_loss);              // train.py:58
+    else tb = ((double)t > a.best_after) && (Ltot < *a.best_loss);                // poc/main.py:414 (Llim starts at 10)
+    take_best = tb ? 1 : 0;
+    if (a.hist && (long long)t < a.hist_cap) {
+      double* h = a.hist + 4 * t;
+      h[0] = Ltot; h[1] = a.sums[1]; h[2] = a.sums[2];
+      h[3] = a.hist_mean_E ? a.sums[3] / (double)a.n : a.sums[7];  // train.py prints mean(e); poc keeps E[-1]
+    }
+  }
+  __syncthreads();
+  const double tt = (double)(t + 1ull);
+  const double bc1 = 1.0 - pow(a.beta1, tt), bc2 = 1.0 - pow(a.beta2, tt);
+  const double step_size = a.lr / bc1, bc2_sqrt = sqrt(bc2);
+  const int offs[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
+                        O_WGL, O_BGL, O_WG, O_BG, NTHETA};
+  for (int i = threadIdx.x; i < NTHETA; i += blockDim.x) {
+    int ti = 0;
+#pragma unroll
+    for (int k = 1; k < 16; k++) ti += (i >= offs[k]);
+    double th = a.theta[i];
+    if (take_best && a.best_mode == 0) a.best_theta[i] = th;  // train.py keeps the parameters the loss was evaluated at
+    if ((a.grad_mask >> ti) & 1u) {                            // frozen tensors have no gradient: the optimizer skips them
+      const double g = a.grad[i];
+      double m = a.m[i], v = a.v[i];
+      m = m + (g - m) * (1.0 - a.beta1);
+      v = v * a.beta2 + ((1.0 - a.beta2) * g) * g;
+      const double denom = sqrt(v) / bc2_sqrt + a.eps;
+      th = th - step_size * (m / denom);
+      a.m[i] = m; a.v[i] = v; a.theta[i] = th;
+    }
+    if (take_best && a.best_mode == 1) a.best_theta[i] = th;  // poc saves the model after optimizer.step()
+    a.theta32[i] = (float)th;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (take_best) { *a.best_loss = Ltot; *a.best_step = (long long)t; }
+    *a.step = t + 1ull;
+  }
+}
+
+cudaError_t launch_adam(const AdamParams& a, cudaStream_t st) {
+  adam_kernel<<<1, 1024, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// E(R), dE/dR, d2E/dR2 (forward-mode through the 1-32-32-1 E-net) and the gate g(R); one thread per R
+// ---------------------------------------------------------------------------------------------
+__global__ void enet_curve_kernel(const float* __restrict__ th, const double* __restrict__ R, int n, double* __restrict__ E,
+                                  double* __restrict__ dE, double* __restrict__ d2E, double* __restrict__ gate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = R[i];
+  double e1[NE], e1p[NE], e1pp[NE];
+  for (int k = 0; k < NE; k++) {
+    const double w = th[O_WE1 + k], u = w * r + (double)th[O_BE1 + k];
+    const double s = 1.0 / (1.0 + exp(-u)), sp = s * (1.0 - s), spp = sp * (1.0 - 2.0 * s);
+    e1[k] = s; e1p[k] = sp * w; e1pp[k] = spp * w * w;
+  }
+  double Ev = th[O_BE], Ep = 0.0, Epp = 0.0;
+  for (int j = 0; j < NE; j++) {
+    double u = th[O_BE2 + j], up = 0.0, upp = 0.0;
+    for (int k = 0; k < NE; k++) {
+      const double w = th[O_WE2 + j * NE + k];
+      u += w * e1[k]; up += w * e1p[k]; upp += w * e1pp[k];
+    }
+    const double s = 1.0 / (1.0 + exp(-u)), sp = s * (1.0 - s), spp = sp * (1.0 - 2.0 * s);
+    const double wE = th[O_WE + j];
+    Ev += wE * s; Ep += wE * sp * up; Epp += wE * (spp * up * up + sp * upp);
+  }
+  if (E) E[i] = Ev;
+  if (dE) dE[i] = Ep;
+  if (d2E) d2E[i] = Epp;
+  if (gate) {
+    double g = th[O_BG];
+    for (int k = 0; k < NL; k++) {
+      const double u = (double)th[O_WGL + k] * r + (double)th[O_BGL + k];
+      g += (double)th[O_WG + k] / (1.0 + exp(-u));
+    }
+    gate[i] = g;
+  }
+}
+
+cudaError_t launch_enet_curve(const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
+                              cudaStream_t st) {
+  enet_curve_kernel<<<(n + 127) / 128, 128, 0, st>>>(theta, R, n, E, dE, d2E, gate);
+  return cudaGetLastError();
+}
+
+}  // namespace pinn

@@ -1,0 +1,329 @@
+// C ABI of the rows next to the hot path (include/pinn_b200.h, "training loop" and "analysis" sections):
+// sampler, fused Adam, the device-resident trainer (CUDA-graph replay of sample -> loss -> Adam), the E(R)/gate
+// curve and the dense-grid quadrature sums.
+#include <cstdlib>
+#include <cstring>
+
+#include "pinn_handle.h"
+#include "pinn_train.h"
+
+namespace {
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+}  // namespace
+
+struct pinn_trainer {
+  pinn_handle* h = nullptr;
+  pinn_train_config cfg{};
+  cudaStream_t st = nullptr;
+  float *x = nullptr, *y = nullptr, *z = nullptr, *R = nullptr, *E = nullptr, *theta32 = nullptr;
+  uint8_t* mask = nullptr;
+  unsigned long long *counts = nullptr, *batch = nullptr, *step = nullptr;
+  long long* best_step = nullptr;
+  double *weights = nullptr, *theta = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr, *sums = nullptr;
+  double *best_loss = nullptr, *best_theta = nullptr, *hist = nullptr;
+  cudaGraphExec_t g_resample = nullptr, g_keep = nullptr;
+  int64_t steps_issued = 0;
+  bool have_batch = false;
+};
+
+static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
+  pinn_handle* h = t->h;
+  const pinn_train_config& c = t->cfg;
+  if (resample) {
+    SampleParams s{};
+    s.n = c.n; s.seed = c.seed; s.batch_counter = t->batch;
+    s.xL = c.xL; s.xR = c.xR; s.yL = c.yL; s.yR = c.yR; s.zL = c.zL; s.zR = c.zR; s.RL = c.RL; s.RR = c.RR;
+    s.cutoff = c.cutoff; s.bcutoff = c.bcutoff;
+    s.x = t->x; s.y = t->y; s.z = t->z; s.R = t->R; s.mask = t->mask; s.counts = t->counts;
+    CU(h, launch_sample(s, t->weights, st));
+    h->launches += 2;
+  }
+  int rc = pinn_loss_fwd_bwd(h, c.variant, c.n, t->x, t->y, t->z, t->R, PINN_F32, t->mask, t->theta32, t->weights,
+                             c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, (void*)st);
+  if (rc) return rc;
+  AdamParams a{};
+  a.theta = t->theta; a.m = t->m; a.v = t->v; a.grad = t->grad; a.sums = t->sums; a.theta32 = t->theta32;
+  a.step = t->step; a.best_loss = t->best_loss; a.best_theta = t->best_theta; a.best_step = t->best_step;
+  a.hist = t->hist; a.hist_cap = c.history_capacity; a.n = c.n;
+  a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.eps; a.best_after = (double)c.best_after;
+  a.grad_mask = c.grad_mask; a.best_mode = c.best_mode; a.hist_mean_E = c.history_mean_E;
+  CU(h, launch_adam(a, st));
+  h->launches += 1;
+  return 0;
+}
+
+static int trainer_capture(pinn_trainer* t, bool resample, cudaGraphExec_t* out) {
+  pinn_handle* h = t->h;
+  cudaGraph_t g = nullptr;
+  CU(h, cudaStreamBeginCapture(t->st, cudaStreamCaptureModeThreadLocal));
+  const int64_t launches_before = h->launches;
+  int rc = trainer_enqueue(t, resample, t->st);
+  h->launches = launches_before;  // capture does not launch; replays are counted in pinn_trainer_run
+  cudaError_t e = cudaStreamEndCapture(t->st, &g);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(h, (int)e, "cudaStreamEndCapture");
+  e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(h, (int)e, "cudaGraphInstantiate");
+  return 0;
+}
+
+extern "C" {
+
+int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const float box[8], float cutoff, float bcutoff,
+                float* x, float* y, float* z, float* R, uint8_t* mask, uint64_t* counts, double* weights, void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n <= 0 || !box || !x || !y || !z || !R || !mask || !counts || !weights)
+    return fail(h, PINN_EINVAL, "pinn_sample: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  set_u64_kernel<<<1, 1, 0, st>>>(h->batch_counter, (unsigned long long)batch);
+  SampleParams s{};
+  s.n = n; s.seed = seed; s.batch_counter = h->batch_counter;
+  s.xL = box[0]; s.xR = box[1]; s.yL = box[2]; s.yR = box[3]; s.zL = box[4]; s.zR = box[5]; s.RL = box[6]; s.RR = box[7];
+  s.cutoff = cutoff; s.bcutoff = bcutoff;
+  s.x = x; s.y = y; s.z = z; s.R = R; s.mask = mask; s.counts = (unsigned long long*)counts;
+  CU(h, launch_sample(s, weights, st));
+  h->launches += 3;
+  return 0;
+}
+
+int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const double* grad, const double* sums, float* theta32,
+                   uint64_t* step, double* best_loss, double* best_theta, int64_t* best_step, double* hist, int64_t hist_cap,
+                   int64_t n, double lr, double beta1, double beta2, double eps, uint32_t grad_mask, int best_mode,
+                   int64_t best_after, int history_mean_E, void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!theta || !m || !v || !grad || !sums || !theta32 || !step || !best_loss || !best_theta || !best_step)
+    return fail(h, PINN_EINVAL, "pinn_adam_step: NULL pointer argument");
+  CU(h, cudaSetDevice(h->device));
+  AdamParams a{};
+  a.theta = theta; a.m = m; a.v = v; a.grad = grad; a.sums = sums; a.theta32 = theta32;
+  a.step = (unsigned long long*)step; a.best_loss = best_loss; a.best_theta = best_theta; a.best_step = (long long*)best_step;
+  a.hist = hist; a.hist_cap = hist_cap; a.n = n; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.best_after = (double)best_after; a.grad_mask = grad_mask; a.best_mode = best_mode; a.hist_mean_E = history_mean_E;
+  CU(h, launch_adam(a, (cudaStream_t)stream));
+  h->launches += 1;
+  return 0;
+}
+
+int pinn_enet_curve(pinn_handle* h, const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
+                    void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!theta || !R || n <= 0) return fail(h, PINN_EINVAL, "pinn_enet_curve: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, launch_enet_curve(theta, R, n, E, dE, d2E, gate, (cudaStream_t)stream));
+  h->launches += 1;
+  return 0;
+}
+
+int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, int ny, int nz, const double lim[6], double R,
+                     const double* wx, const double* wy, const double* wz, double* out, void* stream) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!theta || !lim || !wx || !wy || !wz || !out) return fail(h, PINN_EINVAL, "pinn_grid_reduce: NULL pointer argument");
+  if (nx < 2 || ny < 2 || nz < 2) return fail(h, PINN_EINVAL, "pinn_grid_reduce: every axis needs at least 2 points");
+  StepParams p{};
+  int nev = 0;
+  if (variant == PINN_VARIANT_POC) { p.vc = {1.0f, -0.5f, -1.0f, -1.0f}; nev = 2; }
+  else if (variant == PINN_VARIANT_TRAINPY) { p.vc = {2.0f, 1.0f, 1.0f, 1.0f}; nev = 1; }
+  else return fail(h, PINN_EINVAL, "pinn_grid_reduce: unknown variant");
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  p.n = (long long)nx * ny * nz;
+  p.wts = h->wts;
+  p.grid.on = 1; p.grid.nx = nx; p.grid.ny = ny; p.grid.nz = nz;
+  p.grid.x0 = lim[0]; p.grid.dx = (lim[1] - lim[0]) / (nx - 1);
+  p.grid.y0 = lim[2]; p.grid.dy = (lim[3] - lim[2]) / (ny - 1);
+  p.grid.z0 = lim[4]; p.grid.dz = (lim[5] - lim[4]) / (nz - 1);
+  p.grid.R = R; p.grid.wx = wx; p.grid.wy = wy; p.grid.wz = wz; p.grid.partials = h->grid_partials;
+  const long long tiles = (p.n + 127) / 128;
+  const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  CU(h, launch_prep(theta, h->wts, st));
+  CU(h, launch_step_tc(nev, false, p, grid, st));  // the dense-grid mode lives in the tcgen05 kernel
+  CU(h, launch_grid_finish(h->grid_partials, grid, out, st));
+  h->launches += 3;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident trainer
+// ---------------------------------------------------------------------------------------------
+int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const double* theta0_host, pinn_trainer** out) {
+  if (!h) return PINN_EINVAL;
+  if (!cfg || !theta0_host || !out) return fail(h, PINN_EINVAL, "pinn_trainer_create: NULL pointer argument");
+  if (cfg->n <= 0 || cfg->sc_sampling <= 0 || cfg->history_capacity < 0)
+    return fail(h, PINN_EINVAL, "pinn_trainer_create: n and sc_sampling must be positive");
+  if (cfg->variant != PINN_VARIANT_POC && cfg->variant != PINN_VARIANT_TRAINPY)
+    return fail(h, PINN_EINVAL, "pinn_trainer_create: unknown variant");
+  CU(h, cudaSetDevice(h->device));
+  pinn_trainer* t = new pinn_trainer();
+  t->h = h; t->cfg = *cfg;
+  *out = nullptr;
+  const size_t n = (size_t)cfg->n;
+  CU(h, cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+  CU(h, cudaMalloc(&t->x, n * 4)); CU(h, cudaMalloc(&t->y, n * 4)); CU(h, cudaMalloc(&t->z, n * 4));
+  CU(h, cudaMalloc(&t->R, n * 4)); CU(h, cudaMalloc(&t->E, n * 4)); CU(h, cudaMalloc(&t->mask, n));
+  CU(h, cudaMalloc(&t->theta32, NPART * 4));
+  CU(h, cudaMalloc(&t->counts, 16)); CU(h, cudaMalloc(&t->batch, 8)); CU(h, cudaMalloc(&t->step, 8)); CU(h, cudaMalloc(&t->best_step, 8));
+  CU(h, cudaMalloc(&t->weights, 4 * 8));
+  CU(h, cudaMalloc(&t->theta, NPART * 8)); CU(h, cudaMalloc(&t->m, NPART * 8)); CU(h, cudaMalloc(&t->v, NPART * 8));
+  CU(h, cudaMalloc(&t->grad, NPART * 8)); CU(h, cudaMalloc(&t->sums, 8 * 8));
+  CU(h, cudaMalloc(&t->best_loss, 8)); CU(h, cudaMalloc(&t->best_theta, NPART * 8));
+  if (cfg->history_capacity > 0) {
+    CU(h, cudaMalloc(&t->hist, (size_t)cfg->history_capacity * 4 * 8));
+    CU(h, cudaMemset(t->hist, 0, (size_t)cfg->history_capacity * 4 * 8));
+  }
+  CU(h, cudaMemset(t->m, 0, NPART * 8)); CU(h, cudaMemset(t->v, 0, NPART * 8));
+  CU(h, cudaMemset(t->batch, 0, 8)); CU(h, cudaMemset(t->step, 0, 8));
+  const long long neg1 = -1;
+  CU(h, cudaMemcpy(t->best_step, &neg1, 8, cudaMemcpyHostToDevice));
+  const double llim = 10.0;  // poc/main.py:370 Llim = 10; train.py takes the first loss unconditionally
+  CU(h, cudaMemcpy(t->best_loss, &llim, 8, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(t->theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(t->best_theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
+  float th32[NTHETA];
+  for (int i = 0; i < NTHETA; i++) th32[i] = (float)theta0_host[i];
+  CU(h, cudaMemcpy(t->theta32, th32, NTHETA * 4, cudaMemcpyHostToDevice));
+  *out = t;
+  return 0;
+}
+
+int pinn_trainer_destroy(pinn_trainer* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->h->device);
+  if (t->st) cudaStreamSynchronize(t->st);
+  if (t->g_resample) cudaGraphExecDestroy(t->g_resample);
+  if (t->g_keep) cudaGraphExecDestroy(t->g_keep);
+  cudaFree(t->x); cudaFree(t->y); cudaFree(t->z); cudaFree(t->R); cudaFree(t->E); cudaFree(t->mask); cudaFree(t->theta32);
+  cudaFree(t->counts); cudaFree(t->batch); cudaFree(t->step); cudaFree(t->best_step); cudaFree(t->weights);
+  cudaFree(t->theta); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad); cudaFree(t->sums);
+  cudaFree(t->best_loss); cudaFree(t->best_theta); cudaFree(t->hist);
+  if (t->st) cudaStreamDestroy(t->st);
+  delete t;
+  return 0;
+}
+
+// Optimizer state / a resumed run: theta, m, v are 1521 host doubles (m, v may be NULL = zeros), `step` optimizer steps done.
+int pinn_trainer_load_state(pinn_trainer* t, const double* theta, const double* m, const double* v, int64_t step) {
+  if (!t) return PINN_EINVAL;
+  pinn_handle* h = t->h;
+  if (!theta || step < 0) return fail(h, PINN_EINVAL, "pinn_trainer_load_state: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(t->st));
+  CU(h, cudaMemcpy(t->theta, theta, NTHETA * 8, cudaMemcpyHostToDevice));
+  float th32[NTHETA];
+  for (int i = 0; i < NTHETA; i++) th32[i] = (float)theta[i];
+  CU(h, cudaMemcpy(t->theta32, th32, NTHETA * 4, cudaMemcpyHostToDevice));
+  if (m) CU(h, cudaMemcpy(t->m, m, NTHETA * 8, cudaMemcpyHostToDevice)); else CU(h, cudaMemset(t->m, 0, NPART * 8));
+  if (v) CU(h, cudaMemcpy(t->v, v, NTHETA * 8, cudaMemcpyHostToDevice)); else CU(h, cudaMemset(t->v, 0, NPART * 8));
+  const unsigned long long s = (unsigned long long)step;
+  CU(h, cudaMemcpy(t->step, &s, 8, cudaMemcpyHostToDevice));
+  t->steps_issued = step;
+  return 0;
+}
+
+// Caller-provided batch instead of the sampler (parity runs feed the reference's own points): device float32 columns,
+// mask bytes and the weights {1/n, 1/|set1|, 1/|set2|}; stays in use until the next resampling step.
+int pinn_trainer_set_batch(pinn_trainer* t, const float* x, const float* y, const float* z, const float* R, const uint8_t* mask,
+                           const double* weights_host) {
+  if (!t) return PINN_EINVAL;
+  pinn_handle* h = t->h;
+  if (!x || !y || !z || !R || !mask || !weights_host) return fail(h, PINN_EINVAL, "pinn_trainer_set_batch: NULL pointer argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)t->cfg.n;
+  CU(h, cudaMemcpyAsync(t->x, x, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->y, y, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->z, z, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->R, R, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->mask, mask, n, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->weights, weights_host, 3 * 8, cudaMemcpyDefault, t->st));
+  CU(h, cudaStreamSynchronize(t->st));
+  t->have_batch = true;
+  return 0;
+}
+
+// Enqueue `steps` optimizer steps.  Step tt resamples iff tt % sc_sampling == 0 and tt < freeze_after (poc/main.py:396;
+// train.py:25) - or never, when resample == 0 (the batch of pinn_trainer_set_batch is kept).  use_graph: replay two
+// captured CUDA graphs (sample+loss+Adam / loss+Adam) instead of launching the 7 kernels of a step one by one.
+int pinn_trainer_run(pinn_trainer* t, int64_t steps, int resample, int use_graph) {
+  if (!t) return PINN_EINVAL;
+  pinn_handle* h = t->h;
+  if (steps < 0) return fail(h, PINN_EINVAL, "pinn_trainer_run: steps must be >= 0");
+  if (!resample && !t->have_batch) return fail(h, PINN_EINVAL, "pinn_trainer_run: no batch yet (resample = 0 needs pinn_trainer_set_batch or an earlier sampled step)");
+  CU(h, cudaSetDevice(h->device));
+  if (use_graph && !t->g_keep) {
+    // one plain step first: one-time kernel attributes are set outside the capture
+    if (steps == 0) return 0;
+    const bool rs = resample && (t->steps_issued % t->cfg.sc_sampling == 0) && (t->steps_issued < t->cfg.freeze_after);
+    int rc = trainer_enqueue(t, rs, t->st);
+    if (rc) return rc;
+    if (rs) t->have_batch = true;
+    t->steps_issued++;
+    steps--;
+    CU(h, cudaStreamSynchronize(t->st));
+    rc = trainer_capture(t, true, &t->g_resample);
+    if (rc) return rc;
+    rc = trainer_capture(t, false, &t->g_keep);
+    if (rc) return rc;
+  }
+  for (int64_t k = 0; k < steps; k++) {
+    const int64_t tt = t->steps_issued;
+    const bool rs = resample && (tt % t->cfg.sc_sampling == 0) && (tt < t->cfg.freeze_after);
+    if (use_graph) {
+      CU(h, cudaGraphLaunch(rs ? t->g_resample : t->g_keep, t->st));
+      h->launches += rs ? 7 : 5;
+    } else {
+      int rc = trainer_enqueue(t, rs, t->st);
+      if (rc) return rc;
+    }
+    if (rs) t->have_batch = true;
+    t->steps_issued++;
+  }
+  return 0;
+}
+
+// Synchronise and read back.  Any pointer may be NULL.  scalars: {steps done, best loss, best step, batches drawn}.
+int pinn_trainer_read(pinn_trainer* t, double* theta, double* m, double* v, double* best_theta, double* scalars, double* history,
+                      int64_t history_rows) {
+  if (!t) return PINN_EINVAL;
+  pinn_handle* h = t->h;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(t->st));
+  if (theta) CU(h, cudaMemcpy(theta, t->theta, NTHETA * 8, cudaMemcpyDeviceToHost));
+  if (m) CU(h, cudaMemcpy(m, t->m, NTHETA * 8, cudaMemcpyDeviceToHost));
+  if (v) CU(h, cudaMemcpy(v, t->v, NTHETA * 8, cudaMemcpyDeviceToHost));
+  if (best_theta) CU(h, cudaMemcpy(best_theta, t->best_theta, NTHETA * 8, cudaMemcpyDeviceToHost));
+  if (scalars) {
+    unsigned long long s = 0, b = 0;
+    long long bs = 0;
+    double bl = 0.0;
+    CU(h, cudaMemcpy(&s, t->step, 8, cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&b, t->batch, 8, cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&bs, t->best_step, 8, cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&bl, t->best_loss, 8, cudaMemcpyDeviceToHost));
+    scalars[0] = (double)s; scalars[1] = bl; scalars[2] = (double)bs; scalars[3] = (double)b;
+  }
+  if (history && history_rows > 0) {
+    const int64_t rows = history_rows < t->cfg.history_capacity ? history_rows : t->cfg.history_capacity;
+    if (rows > 0) CU(h, cudaMemcpy(history, t->hist, (size_t)rows * 4 * 8, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// Device pointers of the current batch (x, y, z, R float32; mask bytes), e.g. to inspect what the sampler drew.
+int pinn_trainer_batch(pinn_trainer* t, float** x, float** y, float** z, float** R, uint8_t** mask) {
+  if (!t) return PINN_EINVAL;
+  if (x) *x = t->x;
+  if (y) *y = t->y;
+  if (z) *z = t->z;
+  if (R) *R = t->R;
+  if (mask) *mask = t->mask;
+  return 0;
+}
+
+void* pinn_trainer_stream(pinn_trainer* t) { return t ? (void*)t->st : nullptr; }
+
+}  // extern "C"
