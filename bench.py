@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 18, help="collocation points per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "ffma"],
+                    help="implementation of the fused step kernel (include/pinn_b200.h: pinn_set_engine)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -168,6 +170,7 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     h = pk.Handle.get(local)
+    h.set_engine(args.engine)
 
     theta = torch.from_numpy(load_theta().astype(np.float32)).to(dev)
     host_batches = [synth_batch(n, 1000 * rank + b).pin_memory() for b in range(N_BATCHES)]
@@ -228,10 +231,12 @@ def main():
     P = lambda a: ctypes.c_void_p(a.ctypes.data)
     TP = lambda t: ctypes.c_void_p(t.data_ptr())
 
+    wts_h = [np.ascontiguousarray(w.cpu().numpy()) for w in wts]   # the caller's sampler knows the set sizes
+
     def e2e_step(i):
         b = host_batches[i % N_BATCHES]
-        rc = h.L.pinn_loss_fwd_bwd_host(h.h, 0, n, TP(b[0]), TP(b[1]), TP(b[2]), TP(b[3]), 0, None, P(th64), None,
-                                        0xFFFF, 17.5, P(sums_h), P(dth_h), None)
+        rc = h.L.pinn_loss_fwd_bwd_host(h.h, 0, n, TP(b[0]), TP(b[1]), TP(b[2]), TP(b[3]), 0, None, P(th64),
+                                        P(wts_h[i % N_BATCHES]), 0xFFFF, 17.5, P(sums_h), P(dth_h), None)
         h.check(rc, "pinn_loss_fwd_bwd_host")
         if world > 1:
             out[:8] = torch.from_numpy(sums_h).to(dev)
@@ -251,6 +256,23 @@ def main():
     if world > 1:
         dist.all_reduce(tte, op=dist.ReduceOp.MAX)
     te = float(tte.item())
+
+    # ---- the whole training loop on the device (sampler -> loss/gradient -> Adam, CUDA-graph replay): N=1 only
+    loop = None
+    if world == 1:
+        tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6)
+        tr.run(20)
+        tr.read()
+        Kl = max(10, min(K, 300))
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = torch.cuda.ExternalStream(tr.h.L.pinn_trainer_stream(tr.t), device=dev)
+        l0.record(ts)
+        tr.run(Kl)
+        l1.record(ts)
+        tr.read()
+        loop = {"value": n * Kl / (l0.elapsed_time(l1) * 1e-3), "unit": "points/s", "steps": Kl,
+                "what": "pinn_trainer: Philox sampler + fused loss/gradient + float64 Adam per step, one CUDA-graph replay each, no host sync"}
+        tr.close()
 
     if rank == 0:
         total_points = float(n) * world
@@ -274,13 +296,16 @@ def main():
                          "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_MEASURED,
                          "frac_of_nominal_74.4": achieved / FP32_PEAK_NOMINAL,
                          "peak_source": "measured FFMA rate on this pool's B200 (tools/microbench/pipes.cu); MEASURED_PEAKS.json has no FP32 entry",
-                         "flop_per_point": FLOP_PER_POINT, "kernel": "pinn_step_kernel<2,G,true>",
+                         "flop_per_point": FLOP_PER_POINT, "engine": args.engine,
+                         "kernel": "pinn_step_tc_kernel<2,true>" if args.engine == "tcgen05" else "pinn_step_kernel<2,4,true>",
                          "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic},
             "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
                     "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke,
-                    "api": "pinn_loss_fwd_bwd_host (pinned float32 host batches)"},
+                    "api": "pinn_loss_fwd_bwd_host (pinned float32 host batches, up to 4 chunks: the H2D of chunk k+1 overlaps the kernel of chunk k)"},
             "gpu_launches": int(launches), "clocks": clocks, "loss": loss,
         }
+        if loop:
+            line["device_train_loop"] = loop
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}

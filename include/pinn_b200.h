@@ -125,7 +125,7 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n,
 /*
  * Same as pinn_loss_fwd_bwd but with HOST buffers (the call a CPU-resident caller such
  * as the unmodified reference training loop makes): copies the coordinates host->device
- * in chunks on two streams so copies overlap the kernel, runs the step, copies the 8 sums
+ * in up to 4 chunks on a copy stream so that copies overlap the kernels (when weights_host is given), runs the step, copies the 8 sums
  * and 1521 gradients back and synchronises.  theta_host is 1521 double (the reference keeps
  * parameters in float64); weights_host is 3 double or NULL.  Pinned host memory is faster but
  * not required.

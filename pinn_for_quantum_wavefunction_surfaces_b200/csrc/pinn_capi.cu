@@ -53,6 +53,7 @@ int pinn_create(int device, pinn_handle** out) {
   CU(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   CU(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   CU(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  for (int c = 0; c < 4; c++) CU(h, cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -66,6 +67,7 @@ int pinn_destroy(pinn_handle* h) {
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  for (int c = 0; c < 4; c++) if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -126,6 +128,37 @@ static cudaError_t launch_step_any(pinn_handle* h, int nev, bool train, const St
   return h->engine == PINN_ENGINE_TCGEN05 ? launch_step_tc(nev, train, p, grid, st) : launch_step(nev, train, p, grid, st);
 }
 
+// Enqueue the fused step kernel for points [first, first + cnt) of a batch; its per-CTA rows go to partial rows
+// [row0, row0 + *rows).  The handle mutex is held by the caller.
+static int enqueue_step_chunk(pinn_handle* h, int nev, StepParams p, int64_t first, int64_t cnt, int row0, int* rows,
+                              cudaStream_t st) {
+  const size_t es = p.in_f64 ? 8 : 4;
+  p.x = (const char*)p.x + first * es; p.y = (const char*)p.y + first * es;
+  p.z = (const char*)p.z + first * es; p.R = (const char*)p.R + first * es;
+  if (p.mask) p.mask += first;
+  if (p.E_out) p.E_out += first;
+  p.n = cnt;
+  p.partials = h->partials + (size_t)row0 * NPART;
+  const int grid = grid_for(h, cnt);
+  if (row0 + grid > h->max_rows) return fail(h, PINN_EINVAL, "internal: partial-row workspace exceeded");
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling) {
+    while (h->ev_pool.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      CU(h, cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+    e0 = h->ev_pool[h->ev_used++];
+    e1 = h->ev_pool[h->ev_used++];
+    CU(h, cudaEventRecord(e0, st));
+  }
+  CU(h, launch_step_any(h, nev, true, p, grid, st));
+  if (e1) CU(h, cudaEventRecord(e1, st));
+  h->launches++;
+  *rows = grid;
+  return 0;
+}
+
 int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
                       const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
                       uint32_t grad_mask, float bcutoff, double* sums, double* dtheta, float* E_out, void* stream) {
@@ -152,21 +185,9 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
     weights = h->weights_dev;
   }
   p.weights = weights;
-  const int grid = grid_for(h, n);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profiling) {
-    while (h->ev_pool.size() < h->ev_used + 2) {
-      cudaEvent_t e;
-      CU(h, cudaEventCreate(&e));
-      h->ev_pool.push_back(e);
-    }
-    e0 = h->ev_pool[h->ev_used++];
-    e1 = h->ev_pool[h->ev_used++];
-    CU(h, cudaEventRecord(e0, st));
-  }
-  CU(h, launch_step_any(h, nev, true, p, grid, st));
-  if (e1) CU(h, cudaEventRecord(e1, st));
-  h->launches++;
+  int grid = 0;
+  int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
+  if (rc) return rc;
   CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, st));
   h->launches++;
   return 0;
@@ -230,19 +251,62 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     CU(h, cudaMemcpyAsync(h->weights_dev, h->weights_pinned, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     wdev = h->weights_dev;
   }
-  CU(h, cudaMemcpyAsync(base + 0 * col, x, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(base + 1 * col, y, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(base + 2 * col, z, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(base + 3 * col, R, (size_t)n * es, cudaMemcpyHostToDevice, st));
-  uint8_t* mdev = nullptr;
-  if (mask) {
-    mdev = (uint8_t*)(base + 4 * col);
-    CU(h, cudaMemcpyAsync(mdev, mask, (size_t)n, cudaMemcpyHostToDevice, st));
+  uint8_t* mdev = mask ? (uint8_t*)(base + 4 * col) : nullptr;
+  float* edev = (float*)(base + 4 * col + mcol);
+  // With the weights known up front the batch is processed in up to 4 chunks so that the copy of chunk k+1 (copy stream)
+  // overlaps the kernel of chunk k.  Chunks are whole rounds of super-tiles (sm_count x 128 points) so that no launch
+  // ends on a partial wave; the first chunk is short (2 rounds) to start computing early.
+  // Without weights the set sizes must be counted over the whole batch first: one chunk.
+  const int64_t unit = (int64_t)h->sm_count * 128;
+  const int64_t rounds = (n + unit - 1) / unit;
+  int nchunk = 1;
+  int64_t first[4] = {0, 0, 0, 0}, cnt[4] = {n, 0, 0, 0};
+  if (weights_host && rounds >= 8) {
+    nchunk = 4;
+    const int64_t rest = rounds - 2;
+    const int64_t r[4] = {2, rest / 3, rest / 3, rest - 2 * (rest / 3)};
+    int64_t at = 0;
+    for (int c = 0; c < 4; c++) {
+      first[c] = at;
+      cnt[c] = (c == 3) ? n - at : r[c] * unit;
+      at += cnt[c];
+    }
   }
-  float* edev = (E_out_host || true) ? (float*)(base + 4 * col + mcol) : nullptr;
-  int rc = pinn_loss_fwd_bwd(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev,
-                             h->theta_dev, wdev, grad_mask, bcutoff, h->out_dev, h->out_dev + 8, edev, st);
-  if (rc) return rc;
+  const void* src[4] = {x, y, z, R};
+  for (int c = 0; c < nchunk; c++) {
+    cudaStream_t sc = nchunk == 1 ? st : h->s_copy;
+    for (int k = 0; k < 4; k++)
+      CU(h, cudaMemcpyAsync(base + k * col + first[c] * es, (const char*)src[k] + first[c] * es, (size_t)cnt[c] * es,
+                            cudaMemcpyHostToDevice, sc));
+    if (mask) CU(h, cudaMemcpyAsync(mdev + first[c], mask + first[c], (size_t)cnt[c], cudaMemcpyHostToDevice, sc));
+    if (nchunk > 1) CU(h, cudaEventRecord(h->ev_chunk[c], sc));
+  }
+  if (nchunk == 1) {
+    int rc = pinn_loss_fwd_bwd(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev,
+                               h->theta_dev, wdev, grad_mask, bcutoff, h->out_dev, h->out_dev + 8, edev, st);
+    if (rc) return rc;
+  } else {
+    std::lock_guard<std::mutex> lk(h->mu);
+    StepParams p{};
+    int nev = 0;
+    if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: unknown variant");
+    p.x = base; p.y = base + col; p.z = base + 2 * col; p.R = base + 3 * col; p.mask = mdev; p.wts = h->wts;
+    p.in_f64 = in_dtype == PINN_F64; p.bcut = bcutoff; p.E_out = edev; p.weights = wdev;
+    p.base_grads = (grad_mask & 0x003Fu) != 0;
+    p.gate_grads = (grad_mask & 0xF000u) != 0;
+    CU(h, launch_prep(h->theta_dev, h->wts, st));
+    h->launches++;
+    int rows = 0;
+    for (int c = 0; c < nchunk; c++) {
+      CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
+      int r = 0;
+      int rc = enqueue_step_chunk(h, nev, p, first[c], cnt[c], rows, &r, st);
+      if (rc) return rc;
+      rows += r;
+    }
+    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, h->out_dev + 8, h->out_dev, edev, n, st));
+    h->launches++;
+  }
   CU(h, cudaMemcpyAsync(h->out_pinned, h->out_dev, (8 + NTHETA) * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));

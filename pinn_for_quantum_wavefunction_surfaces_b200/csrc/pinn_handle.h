@@ -31,6 +31,7 @@ struct pinn_handle {
   double* weights_pinned = nullptr;
   cudaStream_t s_copy = nullptr, s_main = nullptr;
   cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // *_host entry: copy of chunk c complete
   int64_t launches = 0;
   int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
   bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel

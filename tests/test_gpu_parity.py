@@ -27,6 +27,15 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True, params=["tcgen05", "ffma"])
+def engine(request):
+    """every parity test runs on both implementations of the fused step kernel (pinn_set_engine)"""
+    h = pk.Handle.get(0)
+    h.set_engine(request.param)
+    yield request.param
+    h.set_engine("tcgen05")
+
+
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
