@@ -32,7 +32,8 @@ class PinnError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    """The in-tree library; PINN_B200_LIBRARY points development tools (tools/timeline.py) at an instrumented build."""
+    return os.environ.get("PINN_B200_LIBRARY") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None
