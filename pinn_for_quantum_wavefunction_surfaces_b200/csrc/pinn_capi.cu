@@ -10,6 +10,10 @@
 
 std::string g_create_err;
 
+// upload block of the *_host entry: theta as float (padded to 1536) followed by the 3 loss weights
+constexpr int HOST_IN_THETA = 1536;
+constexpr size_t HOST_IN_BYTES = HOST_IN_THETA * sizeof(float) + 4 * sizeof(double);
+
 static const int kOffsets[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
                                  O_WGL, O_BGL, O_WG, O_BG, NTHETA};
 
@@ -39,17 +43,19 @@ int pinn_create(int device, pinn_handle** out) {
     if (!strcmp(e, "ffma")) h->engine = PINN_ENGINE_FFMA;
     else if (!strcmp(e, "tcgen05")) h->engine = PINN_ENGINE_TCGEN05;
   }
+  if (const char* e = getenv("PINN_B200_HOST_ZEROCOPY")) h->host_zero_copy = strcmp(e, "0") != 0;
   CU(h, cudaMalloc(&h->wts, sizeof(Wts)));
-  CU(h, cudaMalloc(&h->theta_dev, NPART * sizeof(float)));
-  CU(h, cudaMalloc(&h->weights_dev, 4 * sizeof(double)));
+  // theta (1536 float) and the 3 loss weights share one block so that the *_host entry uploads both with one copy
+  CU(h, cudaMalloc(&h->theta_dev, HOST_IN_BYTES));
+  h->weights_dev = reinterpret_cast<double*>(h->theta_dev + HOST_IN_THETA);
   CU(h, cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
   CU(h, cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
-  CU(h, cudaMalloc(&h->out_dev, NPART * sizeof(double)));
   CU(h, cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
   CU(h, cudaMalloc(&h->batch_counter, sizeof(unsigned long long)));
-  CU(h, cudaMallocHost(&h->out_pinned, NPART * sizeof(double)));
-  CU(h, cudaMallocHost(&h->theta_pinned, NPART * sizeof(float)));
-  CU(h, cudaMallocHost(&h->weights_pinned, 4 * sizeof(double)));
+  CU(h, cudaHostAlloc(&h->out_pinned, NPART * sizeof(double), cudaHostAllocMapped));
+  CU(h, cudaHostGetDevicePointer(&h->out_mapped, h->out_pinned, 0));
+  CU(h, cudaMallocHost(&h->theta_pinned, HOST_IN_BYTES));
+  h->weights_pinned = reinterpret_cast<double*>(h->theta_pinned + HOST_IN_THETA);
   CU(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
   CU(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   CU(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
@@ -61,9 +67,9 @@ int pinn_create(int device, pinn_handle** out) {
 int pinn_destroy(pinn_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->weights_dev); cudaFree(h->counts);
-  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->out_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
-  cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned); cudaFreeHost(h->weights_pinned);
+  cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->counts);
+  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
+  cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -109,6 +115,15 @@ int pinn_profile_collect(pinn_handle* h, double* total_ms, int* launches) {
   h->profiling = false;
   h->ev_used = 0;
   return 0;
+}
+
+// Device-visible alias of a page-locked host pointer, or false when the memory is pageable / not host memory.
+static bool map_pinned(const void* p, const void** dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+  *dev = a.devicePointer;
+  return true;
 }
 
 static int variant_coef(int variant, VariantCoef* vc, int* nev) {
@@ -226,8 +241,14 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: bad in_dtype");
   CU(h, cudaSetDevice(h->device));
   const size_t es = in_dtype == PINN_F64 ? 8 : 4;
-  const size_t col = ((size_t)n * es + 255) & ~(size_t)255;
-  const size_t mcol = ((size_t)n + 255) & ~(size_t)255;
+  // Page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) inputs are read by the kernel in place: the
+  // step kernel requests the coordinates of its next super-tile one tile ahead, which hides the PCIe latency, and
+  // the 16 B/point crossing the bus overlap the whole kernel instead of preceding it.  Pageable inputs are staged.
+  const void* mapped[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool zero_copy = h->host_zero_copy && map_pinned(x, &mapped[0]) && map_pinned(y, &mapped[1]) &&
+                         map_pinned(z, &mapped[2]) && map_pinned(R, &mapped[3]) && (!mask || map_pinned(mask, &mapped[4]));
+  const size_t col = zero_copy ? 0 : ((size_t)n * es + 255) & ~(size_t)255;
+  const size_t mcol = zero_copy ? 0 : ((size_t)n + 255) & ~(size_t)255;
   const size_t ecol = ((size_t)n * 4 + 255) & ~(size_t)255;
   const size_t need = 4 * col + mcol + ecol;
   {
@@ -244,13 +265,15 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
   char* base = (char*)h->stage_dev;
   cudaStream_t st = h->s_main;
   for (int i = 0; i < NTHETA; i++) h->theta_pinned[i] = (float)theta_host[i];
-  CU(h, cudaMemcpyAsync(h->theta_dev, h->theta_pinned, NTHETA * sizeof(float), cudaMemcpyHostToDevice, st));
   const double* wdev = nullptr;
   if (weights_host) {
     memcpy(h->weights_pinned, weights_host, 3 * sizeof(double));
-    CU(h, cudaMemcpyAsync(h->weights_dev, h->weights_pinned, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     wdev = h->weights_dev;
   }
+  CU(h, cudaMemcpyAsync(h->theta_dev, h->theta_pinned, weights_host ? HOST_IN_BYTES : NTHETA * sizeof(float),
+                        cudaMemcpyHostToDevice, st));
+  // the 8 sums and 1521 gradients are written by the reduction kernel straight into mapped page-locked memory
+  double* outp = h->out_mapped;
   uint8_t* mdev = mask ? (uint8_t*)(base + 4 * col) : nullptr;
   float* edev = (float*)(base + 4 * col + mcol);
   // With the weights known up front the batch is processed in up to 4 chunks so that the copy of chunk k+1 (copy stream)
@@ -272,8 +295,9 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
       at += cnt[c];
     }
   }
+  if (zero_copy) nchunk = 1;
   const void* src[4] = {x, y, z, R};
-  for (int c = 0; c < nchunk; c++) {
+  for (int c = 0; c < nchunk && !zero_copy; c++) {
     cudaStream_t sc = nchunk == 1 ? st : h->s_copy;
     for (int k = 0; k < 4; k++)
       CU(h, cudaMemcpyAsync(base + k * col + first[c] * es, (const char*)src[k] + first[c] * es, (size_t)cnt[c] * es,
@@ -281,9 +305,13 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     if (mask) CU(h, cudaMemcpyAsync(mdev + first[c], mask + first[c], (size_t)cnt[c], cudaMemcpyHostToDevice, sc));
     if (nchunk > 1) CU(h, cudaEventRecord(h->ev_chunk[c], sc));
   }
-  if (nchunk == 1) {
+  if (zero_copy) {
+    int rc = pinn_loss_fwd_bwd(h, variant, n, mapped[0], mapped[1], mapped[2], mapped[3], in_dtype,
+                               (const uint8_t*)mapped[4], h->theta_dev, wdev, grad_mask, bcutoff, outp, outp + 8, edev, st);
+    if (rc) return rc;
+  } else if (nchunk == 1) {
     int rc = pinn_loss_fwd_bwd(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev,
-                               h->theta_dev, wdev, grad_mask, bcutoff, h->out_dev, h->out_dev + 8, edev, st);
+                               h->theta_dev, wdev, grad_mask, bcutoff, outp, outp + 8, edev, st);
     if (rc) return rc;
   } else {
     std::lock_guard<std::mutex> lk(h->mu);
@@ -304,10 +332,9 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
       if (rc) return rc;
       rows += r;
     }
-    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, h->out_dev + 8, h->out_dev, edev, n, st));
+    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, outp + 8, outp, edev, n, st));
     h->launches++;
   }
-  CU(h, cudaMemcpyAsync(h->out_pinned, h->out_dev, (8 + NTHETA) * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));
   memcpy(sums_host, h->out_pinned, 8 * sizeof(double));

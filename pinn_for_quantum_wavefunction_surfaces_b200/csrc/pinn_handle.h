@@ -15,8 +15,8 @@ struct pinn_handle {
   int device = 0;
   int sm_count = 0;
   Wts* wts = nullptr;              // prepared weight image
-  float* theta_dev = nullptr;      // staging for the *_host entry (1536 float)
-  double* weights_dev = nullptr;   // 3 double
+  float* theta_dev = nullptr;      // upload block of the *_host entry: 1536 float ...
+  double* weights_dev = nullptr;   // ... followed by the 3 loss weights (also the output of the set-count kernels)
   unsigned long long* counts = nullptr;
   double* partials = nullptr;      // [max_rows][NPART]
   int max_rows = 0;
@@ -25,8 +25,8 @@ struct pinn_handle {
   // *_host entry
   void* stage_dev = nullptr;       // coordinates + mask
   size_t stage_bytes = 0;
-  double* out_dev = nullptr;       // 8 sums + 1521 grads
-  double* out_pinned = nullptr;
+  double* out_pinned = nullptr;    // mapped page-locked: the reduction kernel of the *_host entry writes it directly
+  double* out_mapped = nullptr;    // its device alias
   float* theta_pinned = nullptr;
   double* weights_pinned = nullptr;
   cudaStream_t s_copy = nullptr, s_main = nullptr;
@@ -34,6 +34,7 @@ struct pinn_handle {
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // *_host entry: copy of chunk c complete
   int64_t launches = 0;
   int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
+  bool host_zero_copy = true;         // pinn_loss_fwd_bwd_host reads page-locked inputs in place (PINN_B200_HOST_ZEROCOPY=0: stage)
   bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;

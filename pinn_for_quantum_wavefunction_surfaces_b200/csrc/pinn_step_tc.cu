@@ -41,7 +41,60 @@ template <int NEV>
 __host__ __device__ constexpr int tc_group_stash_floats() { return NEV * EVAL_STASH + ENET_STASH; }
 template <int NEV>
 __host__ __device__ constexpr size_t tc_smem_bytes() {
-  return WTS_TC_BYTES + 64 /*mbarriers + tmem base*/ + sizeof(float2) * 4 * 2 * 3 * 32 + sizeof(float) * 4 * tc_group_stash_floats<NEV>();
+  return WTS_TC_BYTES + 64 /*mbarriers + tmem base*/ + sizeof(float2) * 4 * 2 * 3 * 32 + sizeof(float) * 4 * tc_group_stash_floats<NEV>() +
+         2 * COORD_STAGE_BYTES;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coordinate stage: the x,y,z,R (and set mask) of the NEXT super-tile travel global -> shared with cp.async while the
+// current one is computed, so that no register (and no warp) waits for them.  This is what lets the host entry hand
+// the kernel page-locked host memory: the PCIe round trip is hidden behind a whole tile of work.
+//   buffer = 4 columns x 128 points x 8 B (float64 inputs; float32 use the first half of each column) + 128 mask words
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// issued by the E-net warp of a group for the group's 32 points (slot = 32 * group + lane of the super-tile)
+__device__ __forceinline__ void coord_stage_issue(const StepParams& p, unsigned char* buf, int slot, long long i) {
+  const uint32_t b = smem_u32(buf);
+  if (p.in_f64) {
+    cp_async8(b + 0 * COORD_COL_BYTES + slot * 8, (const double*)p.x + i);
+    cp_async8(b + 1 * COORD_COL_BYTES + slot * 8, (const double*)p.y + i);
+    cp_async8(b + 2 * COORD_COL_BYTES + slot * 8, (const double*)p.z + i);
+    cp_async8(b + 3 * COORD_COL_BYTES + slot * 8, (const double*)p.R + i);
+  } else {
+    cp_async4(b + 0 * COORD_COL_BYTES + slot * 4, (const float*)p.x + i);
+    cp_async4(b + 1 * COORD_COL_BYTES + slot * 4, (const float*)p.y + i);
+    cp_async4(b + 2 * COORD_COL_BYTES + slot * 4, (const float*)p.z + i);
+    cp_async4(b + 3 * COORD_COL_BYTES + slot * 4, (const float*)p.R + i);
+  }
+  // the aligned 4-byte word that holds mask[i] (allocations are at least 4-byte granular); the reader picks the byte
+  if (p.mask) cp_async4(b + 4 * COORD_COL_BYTES + slot * 4, (const void*)((uintptr_t)(p.mask + i) & ~(uintptr_t)3));
+}
+__device__ __forceinline__ RawPt coord_stage_read(const StepParams& p, const unsigned char* buf, int slot) {
+  RawPt r;
+  if (p.in_f64) {
+    const double xd = *(const double*)(buf + 0 * COORD_COL_BYTES + slot * 8), Rd = *(const double*)(buf + 3 * COORD_COL_BYTES + slot * 8);
+    r.dx1 = (float)(xd - Rd);  // the difference is formed in double so that r near a nucleus keeps its digits
+    r.dx2 = (float)(xd + Rd);
+    r.y = (float)*(const double*)(buf + 1 * COORD_COL_BYTES + slot * 8);
+    r.z = (float)*(const double*)(buf + 2 * COORD_COL_BYTES + slot * 8);
+    r.R = (float)Rd;
+  } else {
+    const float xf = *(const float*)(buf + 0 * COORD_COL_BYTES + slot * 4);
+    r.R = *(const float*)(buf + 3 * COORD_COL_BYTES + slot * 4);
+    r.dx1 = xf - r.R;
+    r.dx2 = xf + r.R;
+    r.y = *(const float*)(buf + 1 * COORD_COL_BYTES + slot * 4);
+    r.z = *(const float*)(buf + 2 * COORD_COL_BYTES + slot * 4);
+  }
+  return r;
 }
 
 __device__ __forceinline__ void tc_role_sync(const TcCtx& c) {
@@ -534,6 +587,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + WTS_TC_BYTES + 32);
   float2* mbox = reinterpret_cast<float2*>(smem_raw + WTS_TC_BYTES + 64);
   float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
+  unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - 2 * COORD_STAGE_BYTES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int role = warp >> 2, grp = warp & 3;
@@ -599,22 +653,29 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   // 32 points lie beyond n compute on a clamped index with zero weight
   const long long nsuper = (p.n + 127) >> 7;
   int it = 0;
-  RawPt nxt;
-  {
-    const long long i0 = (long long)blockIdx.x * 128 + grp * 32 + lane;
-    nxt = tc_load_point(p, i0 < p.n ? i0 : p.n - 1);
+  const int slot = grp * 32 + lane;
+  const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
+  if (stager) {
+    const long long i0 = (long long)blockIdx.x * 128 + slot;
+    coord_stage_issue(p, cstage, slot, i0 < p.n ? i0 : p.n - 1);
+    cp_async_commit();
+    cp_async_wait_all();
   }
+  __syncthreads();
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
-    const long long pidx = st * 128 + grp * 32 + lane;
+    const long long pidx = st * 128 + slot;
     const bool valid = pidx < p.n;
     const long long pi = valid ? pidx : (p.n - 1);
     c.tl_it = it;
     TL(0);
-    const Geom g = geom_from_raw(nxt);
-    const float cur_dx1 = nxt.dx1, cur_dx2 = nxt.dx2;
-    {  // coordinates of the next super-tile: issued now, consumed one iteration later
+    const unsigned char* cbuf = cstage + (it & 1) * COORD_STAGE_BYTES;
+    const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
+    const Geom g = geom_from_raw(raw);
+    const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
+    if (stager) {  // coordinates of the next super-tile: in flight during this one, complete before the group barrier
       const long long in = pidx + (long long)gridDim.x * 128;
-      nxt = tc_load_point(p, in < p.n ? in : p.n - 1);
+      if (st + gridDim.x < nsuper) coord_stage_issue(p, cstage + ((it + 1) & 1) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
+      cp_async_commit();
     }
     float2* box = gbox + (it & 1) * (3 * 32);
 
@@ -635,6 +696,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
       box[2 * 32 + lane] = make_float2(E, gt);
     }
     TL(5);
+    if (stager) cp_async_wait_all();  // next tile's coordinates have landed; the barrier publishes them to the group
     named_barrier(1 + grp, (NEV + 1) * 32);
     TL(6);
 
@@ -691,7 +753,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
     float m1f, m2f;
     if (p.mask) {
-      const unsigned mk = p.mask[pi];
+      const unsigned mk = *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
       m1f = (mk & 1u) ? 1.0f : 0.0f;
       m2f = (mk & 2u) ? 1.0f : 0.0f;
     } else {

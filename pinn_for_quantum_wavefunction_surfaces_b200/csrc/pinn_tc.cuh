@@ -109,6 +109,9 @@ constexpr uint32_t F_V0 = 96, F_V12 = 112, F_P = 144;
 constexpr uint32_t B_VB_HI = 0, B_VB_LO = 64, B_HB = 128;
 constexpr uint32_t E_A_HI = 0, E_A_LO = 32, E_D = 64;
 
+constexpr int COORD_COL_BYTES = 128 * 8;                      // one coordinate column of a super-tile (float64 worst case)
+constexpr int COORD_STAGE_BYTES = 4 * COORD_COL_BYTES + 128 * 4;  // + one word per point for the set mask
+
 constexpr size_t WTS_TC_BYTES = offsetof(Wts, W2);  // everything the tcgen05 kernel stages
 static_assert(WTS_TC_BYTES % 128 == 0, "staged weight image must keep the buffers behind it aligned");
 
@@ -151,8 +154,7 @@ __device__ __forceinline__ void grid_ijk(const GridDesc& g, long long i, int& ix
   iy = (int)(r % g.ny);
   ix = (int)(r / g.ny);
 }
-__device__ __forceinline__ RawPt tc_load_point(const StepParams& p, long long i) {
-  if (!p.grid.on) return load_raw(p, i);
+__device__ __forceinline__ RawPt tc_grid_point(const StepParams& p, long long i) {
   int ix, iy, iz;
   grid_ijk(p.grid, i, ix, iy, iz);
   const double x = fma((double)ix, p.grid.dx, p.grid.x0);

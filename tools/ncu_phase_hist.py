@@ -17,7 +17,7 @@ for r in csv.reader(io.StringIO(raw)):
         d = {k: v for k, v in zip(hdr[4:], r[4:])}
         st = {k.replace("stall_", ""): I(v) for k, v in d.items() if k.startswith("stall_") and "Not Issued" not in k}
         rows.append((int(r[2], 16), r[3].strip(), cur_line, I(d["Instructions Executed"]), I(d["# Samples"]), st))
-rows.sort()
+rows.sort(key=lambda r: r[0])
 tot_s = sum(r[4] for r in rows); tot_i = sum(r[3] for r in rows)
 print("instructions in kernel: %d, executed %d, samples %d" % (len(rows), tot_i, tot_s))
 for b in range(0, len(rows), blk):
