@@ -148,6 +148,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "ffma"],
                     help="implementation of the fused step kernel (include/pinn_b200.h: pinn_set_engine)")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="N>1: sum over ranks fused into the reduction kernel over NVLink peer memory (pinn_dp_*), or a "
+                         "separate NCCL all-reduce per step (the baseline it replaces)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -171,6 +174,9 @@ def main():
     K = args.steps
     h = pk.Handle.get(local)
     h.set_engine(args.engine)
+    fused = world > 1 and args.allreduce == "fused"
+    if fused:
+        dp.attach_fused(h)
 
     theta = torch.from_numpy(load_theta().astype(np.float32)).to(dev)
     host_batches = [synth_batch(n, 1000 * rank + b).pin_memory() for b in range(N_BATCHES)]
@@ -187,7 +193,7 @@ def main():
     def step(i):
         b = dev_batches[i % N_BATCHES]
         pk.loss_and_grad_raw(0, b[0], b[1], b[2], b[3], theta, None, wts[i % N_BATCHES], sums=out[:8], dtheta=out[8:])
-        if world > 1:
+        if world > 1 and not fused:
             dist.all_reduce(out)
 
     def fence():
@@ -238,7 +244,7 @@ def main():
         rc = h.L.pinn_loss_fwd_bwd_host(h.h, 0, n, TP(b[0]), TP(b[1]), TP(b[2]), TP(b[3]), 0, None, P(th64),
                                         P(wts_h[i % N_BATCHES]), 0xFFFF, 17.5, P(sums_h), P(dth_h), None)
         h.check(rc, "pinn_loss_fwd_bwd_host")
-        if world > 1:
+        if world > 1 and not fused:
             out[:8] = torch.from_numpy(sums_h).to(dev)
             out[8:] = torch.from_numpy(dth_h).to(dev)
             dist.all_reduce(out)
@@ -293,7 +299,9 @@ def main():
             "config": {"workload": "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)",
                        "points_per_gpu": n, "global_points": int(total_points), "weights": "models/ionHsym.pt (tests/golden/checkpoints.npz)",
                        "inputs": "%d rotating batches resident in HBM, %.0f MB > 126 MB L2" % (N_BATCHES, N_BATCHES * n * 16 / 1e6),
-                       "parallelism": "dp%d point sharding + 1 all-reduce of 1529 f64" % world if world > 1 else "single GPU"},
+                       "parallelism": ("dp%d point sharding; sum of 1529 f64 over ranks %s" % (
+                           world, "fused into the reduction kernel (NVLink peer stores + flags, pinn_dp_*)" if fused
+                           else "by one NCCL all-reduce per step")) if world > 1 else "single GPU"},
             "roofline": {"bound": "fp32_ffma", "achieved": achieved / 1e12, "peak": FP32_PEAK_MEASURED / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_MEASURED,
                          "frac_of_nominal_74.4": achieved / FP32_PEAK_NOMINAL,
@@ -312,6 +320,9 @@ def main():
             v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
+    if fused:
+        h.dp_status()
+        dp.detach_fused(h)
     if world > 1:
         dist.destroy_process_group()
 

@@ -47,6 +47,7 @@ extern "C" {
 
 #define PINN_EINVAL (-1)  /* bad argument */
 #define PINN_ENOTSUP (-2) /* device is not sm_100 or kernel image missing */
+#define PINN_ETIMEDOUT (-3) /* data-parallel exchange: a peer never delivered */
 
 typedef struct pinn_handle pinn_handle;
 
@@ -135,6 +136,34 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n,
                            const uint8_t* mask, const double* theta_host, const double* weights_host,
                            uint32_t grad_mask, float bcutoff,
                            double* sums_host, double* dtheta_host, float* E_out_host);
+
+/*
+ * Data-parallel exchange (collocation points shard across the GPUs of one box, the 8 sums + 1521
+ * gradients are summed across ranks once per step; the reference has no multi-GPU code, this replaces the
+ * ncclAllReduce a port would add).  The sum is FUSED into the reduction kernel of pinn_loss_fwd_bwd[_host]: each rank
+ * stores its reduced row into every peer's exchange buffer through NVLink peer memory as 8-byte {data, step number}
+ * words (no fence, no separate flag), polls its own buffer for the peers' rows and adds them in rank order
+ * (bit-identical on all ranks).
+ * No extra launch, no host synchronisation, CUDA-graph capturable (the step number lives on the device).
+ * With the exchange enabled the caller passes the GLOBAL loss weights {1/n, 1/|set1|, 1/|set2|} and every rank must
+ * make the same sequence of training-evaluation calls.
+ *
+ *   one process per GPU:  pinn_dp_init(h, rank, world, my_handle)  ->  all-gather the 64-byte handles (any host
+ *                         transport, e.g. torch.distributed)       ->  pinn_dp_connect(h, all_handles)
+ *   one process, several handles/devices:  pinn_dp_init(h_r, r, world, NULL) for all r, then
+ *                         pinn_dp_connect_local(h_r, handles) for all r
+ * pinn_dp_connect* enable the exchange; pinn_dp_enable switches it off/on; pinn_dp_status returns PINN_ETIMEDOUT if a
+ * peer failed to deliver within ~3 s (the kernel then gives up instead of hanging) and the number of completed
+ * exchanges; pinn_dp_shutdown (collective by convention: call it on every rank after a barrier) frees the buffer.
+ */
+#define PINN_DP_HANDLE_BYTES 64
+#define PINN_DP_MAX_WORLD 8
+int pinn_dp_init(pinn_handle* h, int rank, int world, void* ipc_handle_out);
+int pinn_dp_connect(pinn_handle* h, const void* all_handles);
+int pinn_dp_connect_local(pinn_handle* h, pinn_handle* const* peers);
+int pinn_dp_enable(pinn_handle* h, int on);
+int pinn_dp_status(pinn_handle* h, int64_t* exchanges);
+int pinn_dp_shutdown(pinn_handle* h);
 
 /* =====================================================================================================
  * Rows next to the hot path: device-side sampler, fused Adam, a device-resident trainer,

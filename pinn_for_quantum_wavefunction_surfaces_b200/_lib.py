@@ -13,6 +13,7 @@ EXPORTS = [
     "pinn_sample", "pinn_adam_step", "pinn_enet_curve", "pinn_grid_reduce", "pinn_trainer_create", "pinn_trainer_destroy",
     "pinn_trainer_load_state", "pinn_trainer_set_batch", "pinn_trainer_run", "pinn_trainer_read", "pinn_trainer_batch",
     "pinn_trainer_stream",
+    "pinn_dp_init", "pinn_dp_connect", "pinn_dp_connect_local", "pinn_dp_enable", "pinn_dp_status", "pinn_dp_shutdown",
 ]
 
 
@@ -105,6 +106,18 @@ def lib():
         L.pinn_trainer_batch.restype = i32
         L.pinn_trainer_stream.argtypes = [vp]
         L.pinn_trainer_stream.restype = vp
+        L.pinn_dp_init.argtypes = [vp, i32, i32, vp]
+        L.pinn_dp_init.restype = i32
+        L.pinn_dp_connect.argtypes = [vp, vp]
+        L.pinn_dp_connect.restype = i32
+        L.pinn_dp_connect_local.argtypes = [vp, ctypes.POINTER(vp)]
+        L.pinn_dp_connect_local.restype = i32
+        L.pinn_dp_enable.argtypes = [vp, i32]
+        L.pinn_dp_enable.restype = i32
+        L.pinn_dp_status.argtypes = [vp, ctypes.POINTER(i64)]
+        L.pinn_dp_status.restype = i32
+        L.pinn_dp_shutdown.argtypes = [vp]
+        L.pinn_dp_shutdown.restype = i32
         _lib = L
         return L
 
@@ -156,6 +169,37 @@ class Handle:
         ms, k = ctypes.c_double(), ctypes.c_int()
         self.check(self.L.pinn_profile_collect(self.h, ctypes.byref(ms), ctypes.byref(k)), "pinn_profile_collect")
         return ms.value, k.value
+
+    # ---- data-parallel exchange fused into the reduction kernel (include/pinn_b200.h: pinn_dp_*) ----
+    DP_HANDLE_BYTES = 64
+
+    def dp_init(self, rank, world, want_ipc=True):
+        """Allocate this rank's exchange buffer; -> its 64-byte IPC handle (bytes) to be all-gathered."""
+        buf = ctypes.create_string_buffer(self.DP_HANDLE_BYTES)
+        self.check(self.L.pinn_dp_init(self.h, int(rank), int(world), buf if want_ipc else None), "pinn_dp_init")
+        return bytes(buf.raw)
+
+    def dp_connect(self, all_handles):
+        """all_handles: the ranks' IPC handles in rank order (list of 64-byte strings)."""
+        blob = b"".join(all_handles)
+        self.check(self.L.pinn_dp_connect(self.h, ctypes.c_char_p(blob)), "pinn_dp_connect")
+
+    def dp_connect_local(self, handles):
+        """Same process, one Handle per device: handles in rank order."""
+        arr = (ctypes.c_void_p * len(handles))(*[x.h for x in handles])
+        self.check(self.L.pinn_dp_connect_local(self.h, arr), "pinn_dp_connect_local")
+
+    def dp_enable(self, on=True):
+        self.check(self.L.pinn_dp_enable(self.h, 1 if on else 0), "pinn_dp_enable")
+
+    def dp_status(self):
+        """-> number of completed exchanges; raises if a peer timed out."""
+        k = ctypes.c_int64()
+        self.check(self.L.pinn_dp_status(self.h, ctypes.byref(k)), "pinn_dp_status")
+        return int(k.value)
+
+    def dp_shutdown(self):
+        self.check(self.L.pinn_dp_shutdown(self.h), "pinn_dp_shutdown")
 
     def close(self):
         if self.h:

@@ -64,9 +64,22 @@ int pinn_create(int device, pinn_handle** out) {
   return 0;
 }
 
+static void dp_release(pinn_handle* h) {
+  for (int r = 0; r < DP_MAX_WORLD; r++) {
+    if (h->dp_opened[r] && h->dp.peer[r]) cudaIpcCloseMemHandle(h->dp.peer[r]);
+    h->dp_opened[r] = false;
+    h->dp.peer[r] = nullptr;
+  }
+  if (h->dp_buf) cudaFree(h->dp_buf);
+  h->dp_buf = nullptr;
+  h->dp = DpArgs();
+  h->dp_on = false;
+}
+
 int pinn_destroy(pinn_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  dp_release(h);
   cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->counts);
   cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
   cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned);
@@ -124,6 +137,106 @@ static bool map_pinned(const void* p, const void** dev) {
   if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
   *dev = a.devicePointer;
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// data-parallel exchange over NVLink peer memory (include/pinn_b200.h: pinn_dp_*)
+// ---------------------------------------------------------------------------------------------
+int pinn_dp_init(pinn_handle* h, int rank, int world, void* ipc_handle_out) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world)
+    return fail(h, PINN_EINVAL, "pinn_dp_init: need 0 <= rank < world <= 8");
+  CU(h, cudaSetDevice(h->device));
+  dp_release(h);
+  CU(h, cudaMalloc(&h->dp_buf, DP_BUFFER_BYTES));
+  CU(h, cudaMemset(h->dp_buf, 0, DP_BUFFER_BYTES));
+  CU(h, cudaDeviceSynchronize());
+  h->dp.rank = rank;
+  h->dp.world = world;
+  h->dp.peer[rank] = h->dp_buf;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == PINN_DP_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t ih;
+    CU(h, cudaIpcGetMemHandle(&ih, h->dp_buf));
+    memcpy(ipc_handle_out, &ih, sizeof(ih));
+  }
+  return 0;
+}
+
+int pinn_dp_connect(pinn_handle* h, const void* all_handles) {
+  if (!h || !all_handles) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_connect: call pinn_dp_init first");
+  CU(h, cudaSetDevice(h->device));
+  for (int r = 0; r < h->dp.world; r++) {
+    if (r == h->dp.rank) continue;
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, (const char*)all_handles + (size_t)r * PINN_DP_HANDLE_BYTES, sizeof(ih));
+    void* ptr = nullptr;
+    CU(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->dp.peer[r] = (unsigned char*)ptr;
+    h->dp_opened[r] = true;
+  }
+  h->dp_on = true;
+  return 0;
+}
+
+int pinn_dp_connect_local(pinn_handle* h, pinn_handle* const* peers) {
+  if (!h || !peers) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_connect_local: call pinn_dp_init first");
+  CU(h, cudaSetDevice(h->device));
+  for (int r = 0; r < h->dp.world; r++) {
+    if (r == h->dp.rank) continue;
+    pinn_handle* q = peers[r];
+    if (!q || !q->dp_buf || q->dp.world != h->dp.world || q->dp.rank != r)
+      return fail(h, PINN_EINVAL, "pinn_dp_connect_local: peer handle is not initialised for this rank/world");
+    if (q->device != h->device) {
+      int can = 0;
+      CU(h, cudaDeviceCanAccessPeer(&can, h->device, q->device));
+      if (!can) return fail(h, PINN_ENOTSUP, "pinn_dp_connect_local: no peer access between the two devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(h, (int)e, "cudaDeviceEnablePeerAccess");
+    }
+    h->dp.peer[r] = q->dp_buf;
+  }
+  h->dp_on = true;
+  return 0;
+}
+
+int pinn_dp_enable(pinn_handle* h, int on) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (on) {
+    for (int r = 0; r < h->dp.world; r++)
+      if (!h->dp.peer[r]) return fail(h, PINN_EINVAL, "pinn_dp_enable: the exchange is not connected");
+    if (h->dp.world < 1) return fail(h, PINN_EINVAL, "pinn_dp_enable: the exchange is not initialised");
+  }
+  h->dp_on = on != 0;
+  return 0;
+}
+
+int pinn_dp_status(pinn_handle* h, int64_t* exchanges) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_status: the exchange is not initialised");
+  CU(h, cudaSetDevice(h->device));
+  unsigned long long ctl[3];
+  CU(h, cudaMemcpy(ctl, h->dp_buf + DP_ROWS_BYTES, sizeof(ctl), cudaMemcpyDeviceToHost));
+  if (exchanges) *exchanges = (int64_t)ctl[0];
+  if (ctl[2]) return fail(h, PINN_ETIMEDOUT, "pinn_dp: a peer did not deliver its partial sums within the time-out");
+  return 0;
+}
+
+int pinn_dp_shutdown(pinn_handle* h) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaDeviceSynchronize());
+  dp_release(h);
+  return 0;
 }
 
 static int variant_coef(int variant, VariantCoef* vc, int* nev) {
@@ -203,7 +316,7 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
   int grid = 0;
   int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
   if (rc) return rc;
-  CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, st));
+  CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, h->dp_on ? h->dp : DpArgs(), st));
   h->launches++;
   return 0;
 }
@@ -332,7 +445,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
       if (rc) return rc;
       rows += r;
     }
-    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, outp + 8, outp, edev, n, st));
+    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, outp + 8, outp, edev, n, h->dp_on ? h->dp : DpArgs(), st));
     h->launches++;
   }
   if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

@@ -32,6 +32,11 @@ struct pinn_handle {
   cudaStream_t s_copy = nullptr, s_main = nullptr;
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // *_host entry: copy of chunk c complete
+  // data-parallel exchange (pinn_dp_*): own buffer, the peers' buffers as mapped on this device, and whether calls reduce
+  unsigned char* dp_buf = nullptr;
+  DpArgs dp;
+  bool dp_on = false;
+  bool dp_opened[DP_MAX_WORLD] = {false, false, false, false, false, false, false, false};  // peer[r] came from cudaIpcOpenMemHandle
   int64_t launches = 0;
   int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
   bool host_zero_copy = true;         // pinn_loss_fwd_bwd_host reads page-locked inputs in place (PINN_B200_HOST_ZEROCOPY=0: stage)

@@ -726,11 +726,36 @@ __global__ void weights_from_counts_kernel(const unsigned long long* counts, lon
 // ---------------------------------------------------------------------------------------------
 // add the partial rows (fixed order, double) -> dtheta, sums
 // block = 256 threads = 32 entries x 8 row-slices
+//
+// With dp.world > 1 the kernel is also the data-parallel all-reduce, in the style of a low-latency (LL) protocol: every
+// float64 travels as two 8-byte words {32 data bits, 32-bit step number}; 8-byte stores are single-copy atomic, so a
+// reader that sees the step number of this exchange in both words has the value - no fence, no separate flag, one
+// NVLink one-way latency.  Thread (r, e) of block b stores the block's reduced entry e into slot `rank` of peer r's
+// exchange buffer and then polls slot r of its own buffer; the `world` values are added in rank order, so every rank
+// computes bit-identical sums.  No NCCL launch, no extra kernel.  Two slots alternate by step parity: a peer can be at
+// most one exchange ahead (it needs this rank's next contribution to go further).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_relaxed_sys_v2(unsigned int* p, unsigned int a, unsigned int b) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_sys_v2(const unsigned int* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
                                                               const double* __restrict__ weights, uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
-                                                              const float* __restrict__ E_out, long long n) {
+                                                              const float* __restrict__ E_out, long long n, const DpArgs dp) {
   __shared__ double sh[8][33];
   __shared__ double tot[32];
   const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -739,6 +764,55 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   for (int r = sl; r < nrows; r += 8) s += partials[(size_t)r * NPART + idx];
   sh[sl][e] = s;
   __syncthreads();
+  if (dp.world > 1) {
+    unsigned char* own = dp.peer[dp.rank];
+    unsigned long long* ctl = reinterpret_cast<unsigned long long*>(own + DP_ROWS_BYTES);
+    const unsigned long long step64 = ld_acquire_sys(&ctl[0]) + 1;  // ctl[0] = exchanges completed on this rank
+    const unsigned int step = (unsigned int)step64;
+    const size_t slot = (size_t)(step64 & 1ull) * DP_MAX_WORLD;
+    if (sl == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t += sh[i][e];
+      tot[e] = t;
+    }
+    __syncthreads();
+    double v = 0.0;
+    if (sl < dp.world) {
+      const int r = sl;
+      if (r == dp.rank) {
+        v = tot[e];
+      } else {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[e]);
+        unsigned int* dst = reinterpret_cast<unsigned int*>(dp.peer[r]) + ((slot + dp.rank) * NPART + idx) * 4;
+        st_relaxed_sys_v2(dst, (unsigned int)bits, step);
+        st_relaxed_sys_v2(dst + 2, (unsigned int)(bits >> 32), step);
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(own) + ((slot + r) * NPART + idx) * 4;
+        const long long t0 = clock64();
+        uint2 lo, hi;
+        for (;;) {
+          lo = ld_relaxed_sys_v2(src);
+          hi = ld_relaxed_sys_v2(src + 2);
+          if (lo.y == step && hi.y == step) break;
+          if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never arrived; report instead of hanging the GPU
+            ctl[2] = 1ull;
+            break;
+          }
+        }
+        v = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+      }
+    }
+    __syncthreads();  // every thread is done with sh / tot of the local pass
+    sh[sl][e] = v;    // slices >= world contribute 0; the fixed-order sum below is the sum over ranks
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the last block of the launch closes the exchange (the next launch is stream-ordered behind it)
+      __threadfence();
+      if (atomicAdd(&ctl[1], 1ull) == (unsigned long long)gridDim.x - 1) {
+        ctl[1] = 0ull;
+        st_release_sys(&ctl[0], step64);
+      }
+    }
+  }
   if (sl == 0) {
     double t = 0.0;
 #pragma unroll
@@ -810,8 +884,8 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 }
 
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
-                          double* sums, const float* E_out, long long n, cudaStream_t st) {
-  reduce_partials_kernel<<<NPART / 32, 256, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n);
+                          double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st) {
+  reduce_partials_kernel<<<DP_BLOCKS, 256, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
   return cudaGetLastError();
 }
 

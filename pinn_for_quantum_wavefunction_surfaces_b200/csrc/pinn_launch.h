@@ -42,7 +42,21 @@ cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, c
 cudaError_t launch_grid_finish(const double* partials, int nrows, double* out, cudaStream_t st);
 cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st);
 cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st);
+// Data-parallel exchange fused into the reduction kernel: every rank owns one exchange buffer that all
+// peers of the box can write through NVLink peer memory (cudaIpc / peer access).
+//   rows [2 slots][DP_MAX_WORLD][NPART] x 16 B : rank r deposits its reduced row in slot (step & 1), index r, of EVERY
+//        rank; each float64 is two 8-byte words {32 data bits, 32-bit step number} (pinn_kernels.cu: reduce_partials_kernel)
+//   ctl  {exchanges completed, blocks done, status}
+constexpr int DP_MAX_WORLD = 8;
+constexpr int DP_BLOCKS = NPART / 32;
+constexpr size_t DP_ROWS_BYTES = 2ull * DP_MAX_WORLD * NPART * 16;
+constexpr size_t DP_BUFFER_BYTES = DP_ROWS_BYTES + 64;
+struct DpArgs {
+  int world = 0;  // <= 1: no exchange
+  int rank = 0;
+  unsigned char* peer[DP_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // exchange buffers, [rank] = own
+};
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
-                          double* sums, const float* E_out, long long n, cudaStream_t st);
+                          double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st);
 
 }  // namespace pinn

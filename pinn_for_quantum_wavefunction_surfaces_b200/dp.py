@@ -1,5 +1,13 @@
 """Data-parallel step: collocation points shard across ranks, one small all-reduce.
 
+Two ways to do the sum over ranks:
+  * ``attach_fused(handle, group)``: the library's own exchange, FUSED into the reduction kernel of the training evaluation
+    (peer stores over NVLink + release/acquire flags, include/pinn_b200.h pinn_dp_*).  After it every
+    ``ops.loss_and_grad_raw`` / ``pinn_loss_fwd_bwd[_host]`` on that handle returns the GLOBAL sums; no separate collective
+    is launched.  torch.distributed is used once, to all-gather the 64-byte IPC handles.
+  * ``dp_loss_and_grad``: local evaluation followed by ``torch.distributed.all_reduce`` (NCCL on GPUs, gloo in the CPU
+    tests) - the baseline the fused exchange is measured against (bench.py --allreduce nccl).
+
 Each rank evaluates its shard with the GLOBAL weights {1/n, 1/|set1|, 1/|set2|}, so the shard
 results (loss terms, sums, dLtot/dtheta) simply add; one ``all_reduce(SUM)`` over a fused
 float64 buffer of 8 + 1521 scalars finishes the step.  The global set sizes come from one tiny
@@ -46,3 +54,25 @@ def make_gpu_local_step(variant, x, y, z, R, theta, mask=None, grad_mask=0xFFFF)
         ops.loss_and_grad_raw(variant, x, y, z, R, theta, mask, weights, grad_mask, sums=out[:8], dtheta=out[8:])
 
     return step
+
+
+def attach_fused(handle, group=None):
+    """Connect `handle` (one per rank/GPU) to the other ranks of `group` for the fused exchange and enable it.
+
+    Collective: every rank of the group must call it.  Returns the world size."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = handle.dp_init(rank, world)
+    allh = [None] * world
+    dist.all_gather_object(allh, mine, group=group)
+    handle.dp_connect(allh)
+    dist.barrier(group)   # nobody starts exchanging before every peer has mapped every buffer
+    return world
+
+
+def detach_fused(handle, group=None):
+    """Collective teardown of the fused exchange."""
+    import torch
+    torch.cuda.synchronize()
+    dist.barrier(group)
+    handle.dp_shutdown()
