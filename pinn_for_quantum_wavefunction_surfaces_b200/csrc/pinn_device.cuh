@@ -39,10 +39,20 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
 }
 
 // 3xTF32: x = hi + lo.  The tensor cores read the upper 19 bits of an fp32 operand (they truncate; measured with
-// tools/microbench/umma_ts.cu), so hi is x ROUNDED to nearest TF32 (add half an ulp, clear the low 13 bits), lo = x - hi is
-// exact in fp32, and lo gets half an ulp added so that the hardware truncation rounds it to nearest as well.  Unbiased,
-// |error| <= ~2^-22 per product instead of the ~2^-20 (always towards zero) of a plain mask split.
+// tools/microbench/umma_ts.cu).
+//  * weights (split once per step by prep_weights_kernel): split_tf32_rn - hi is x ROUNDED to nearest TF32 (add half an
+//    ulp, clear the low 13 bits), lo = x - hi is exact in fp32 and gets half an ulp added so that the hardware truncation
+//    rounds it to nearest as well: |lo| <= 2^-11 |x| with random sign.
+//  * activations (split per point in the hot loops): split_tf32 - two instructions, hi = the 19 bits the hardware would
+//    read anyway, lo = x - hi exact (the low 13 mantissa bits; the hardware keeps 11 significant bits of them, i.e. loses
+//    at most 2^-22 |x|).  The dropped lo*lo term is <= 2^-21 of the product with the sign of the weight's lo, i.e.
+//    unbiased in the mat-vecs; in the weight-gradient contractions (both operands are activations) it is a common factor
+//    (1 + ~2^-22) on every term of the sum and cancels like the sum itself does.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
 }

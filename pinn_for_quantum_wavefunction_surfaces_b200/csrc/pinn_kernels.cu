@@ -678,7 +678,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ th, Wts* __restric
   // ---- tcgen05 operand images: value -> (hi, lo) TF32 pair ----
   auto put = [](float* hi, float* lo, int off, float v) {
     uint32_t h, l;
-    split_tf32(v, h, l);  // round-to-nearest split, see pinn_device.cuh
+    split_tf32_rn(v, h, l);  // round-to-nearest split, see pinn_device.cuh
     hi[off] = __uint_as_float(h);
     lo[off] = __uint_as_float(l);
   };

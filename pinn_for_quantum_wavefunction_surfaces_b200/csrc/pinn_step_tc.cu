@@ -146,9 +146,9 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       }
     }
     const uint32_t t0 = c.tlane + cb;
-    tc_st_split16(t0 + F_S_HI, t0 + F_S_LO, s_);
-    tc_st_split16(t0 + F_SP_HI, t0 + F_SP_LO, sp_);
-    tc_st_split16(t0 + F_SPP_HI, t0 + F_SPP_LO, spp_);
+    tc_st_split16<true>(t0 + F_S_HI, t0 + F_S_LO, s_);
+    tc_st_split16<true>(t0 + F_SP_HI, t0 + F_SP_LO, sp_);
+    tc_st_split16<true>(t0 + F_SPP_HI, t0 + F_SPP_LO, spp_);
   }
   TL(1);
   tc_role_sync(c);
@@ -272,7 +272,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
     }
     const uint32_t t0 = c.tlane + cb;
 #pragma unroll
-    for (int ch = 0; ch < 4; ch++) tc_st_split16(t0 + B_VB_HI + ch * NH, t0 + B_VB_LO + ch * NH, vbar[ch]);
+    for (int ch = 0; ch < 4; ch++) tc_st_split16<false>(t0 + B_VB_HI + ch * NH, t0 + B_VB_LO + ch * NH, vbar[ch]);
   }
   TL(7);
   tc_role_sync(c);  // (also orders the stash writes above before the fragment loads below: bar.sync)
@@ -410,7 +410,7 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
       e1[k4 + 3] = sigm(fmaf(R, wv.w, bv.w));
       if (STASH) ST4(&E1row[(k16 + k4) ^ sx], e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
     }
-    tc_st_split16(t0 + E_A_HI + k16, t0 + E_A_LO + k16, e1);
+    tc_st_split16<true>(t0 + E_A_HI + k16, t0 + E_A_LO + k16, e1);
   }
   TL(1);
   tc_role_sync(c);
@@ -482,7 +482,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
       for (int i = 0; i < 4; i++) vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
       ST4(&Vrow[(j16 + j4) ^ sx], vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
     }
-    tc_st_split16(t0 + E_A_HI + j16, t0 + E_A_LO + j16, vbar);
+    tc_st_split16<false>(t0 + E_A_HI + j16, t0 + E_A_LO + j16, vbar);
   }
   TL(7);
   tc_role_sync(c);

@@ -85,12 +85,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
-// split 16 values and store them as the hi / lo halves of an A operand row
+// split 16 values and store them as the hi / lo halves of an A operand row.  RN: the round-to-nearest split (forward
+// sweep: psi ~ 1e-8 at the boundary is a cancellation of O(0.1) terms, a common rounding direction of all points would
+// add up in the loss and its gradient); otherwise the two-instruction truncating split (reverse sweep: a common factor
+// 1 - O(2^-22) on a gradient is harmless).  See split_tf32 in pinn_device.cuh.
+template <bool RN>
 __device__ __forceinline__ void tc_st_split16(uint32_t t_hi, uint32_t t_lo, const float (&x)[16]) {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    split_tf32(x[i], hi[i], lo[i]);
+    if (RN) split_tf32_rn(x[i], hi[i], lo[i]);
+    else split_tf32(x[i], hi[i], lo[i]);
   }
   tc_st16(t_hi, hi);
   tc_st16(t_lo, lo);
@@ -114,19 +119,6 @@ constexpr int COORD_STAGE_BYTES = 4 * COORD_COL_BYTES + 128 * 4;  // + one word 
 
 constexpr size_t WTS_TC_BYTES = offsetof(Wts, W2);  // everything the tcgen05 kernel stages
 static_assert(WTS_TC_BYTES % 128 == 0, "staged weight image must keep the buffers behind it aligned");
-
-__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
-}
-// split 8 values and store them as the hi / lo halves of an A operand row
-__device__ __forceinline__ void tc_st_split8(uint32_t t_hi, uint32_t t_lo, const float (&x)[8]) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) split_tf32(x[i], hi[i], lo[i]);
-  tc_st8(t_hi, hi);
-  tc_st8(t_lo, lo);
-}
 
 struct TcCtx {
   uint32_t tbase;      // TMEM base address of the allocation

@@ -14,10 +14,13 @@ for r in rows[2:]:
     toks = src.split()
     op = toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "?")
     op = op.split(".")[0] + ("." + op.split(".")[1] if op.startswith(("LDS", "STS", "MUFU", "SHFL", "LDG", "BAR")) and "." in op else "")
-    n = int(r[iex] or 0); s = int(r[ismp] or 0)
+    try:
+        n = int(r[iex] or 0); s = int(r[ismp] or 0)
+    except ValueError:
+        continue   # header row of the next launch in the report
     ops[op] += n; smp[op] += s; tot += n; tots += s
     for i, h in stall_cols:
-        v = int(r[i] or 0)
+        v = int(r[i] or 0) if (r[i] or "0").lstrip("-").isdigit() else 0
         if v: stall_by_op[op][h] += v
 print("total warp-instructions", tot, "samples", tots)
 for op, n in ops.most_common(28):
