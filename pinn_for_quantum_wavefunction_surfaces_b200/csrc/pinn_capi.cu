@@ -252,6 +252,16 @@ static int grid_for(pinn_handle* h, long long n) {
   return (int)(want < h->sm_count ? (want < 1 ? 1 : want) : h->sm_count);
 }
 
+// The FFMA engine reads a weight image prepared by a small kernel; the tcgen05 engine builds its own from p.theta.
+static int enqueue_prep(pinn_handle* h, const float* theta, StepParams& p, cudaStream_t st) {
+  p.theta = theta;
+  p.wts = h->wts;
+  if (h->engine == PINN_ENGINE_TCGEN05) return 0;
+  CU(h, launch_prep(theta, h->wts, st));
+  h->launches++;
+  return 0;
+}
+
 static cudaError_t launch_step_any(pinn_handle* h, int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
   return h->engine == PINN_ENGINE_TCGEN05 ? launch_step_tc(nev, train, p, grid, st) : launch_step(nev, train, p, grid, st);
 }
@@ -305,8 +315,7 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
   p.bcut = bcutoff; p.partials = h->partials; p.E_out = E_out;
   p.base_grads = (grad_mask & 0x003Fu) != 0;
   p.gate_grads = (grad_mask & 0xF000u) != 0;
-  CU(h, launch_prep(theta, h->wts, st));
-  h->launches++;
+  if (int rc = enqueue_prep(h, theta, p, st)) return rc;
   if (!weights) {
     CU(h, launch_count(p, h->counts, h->weights_dev, st));
     h->launches += 2;
@@ -336,9 +345,9 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const voi
   cudaStream_t st = (cudaStream_t)stream;
   p.x = x; p.y = y; p.z = z; p.R = R; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.psi = psi; p.lap = lap; p.hpsi = hpsi; p.res = res; p.E_out = E;
-  CU(h, launch_prep(theta, h->wts, st));
+  if (int rc = enqueue_prep(h, theta, p, st)) return rc;
   CU(h, launch_step_any(h, nev, false, p, grid_for(h, n), st));
-  h->launches += 2;
+  h->launches++;
   return 0;
 }
 
@@ -435,8 +444,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     p.in_f64 = in_dtype == PINN_F64; p.bcut = bcutoff; p.E_out = edev; p.weights = wdev;
     p.base_grads = (grad_mask & 0x003Fu) != 0;
     p.gate_grads = (grad_mask & 0xF000u) != 0;
-    CU(h, launch_prep(h->theta_dev, h->wts, st));
-    h->launches++;
+    if (int rc = enqueue_prep(h, h->theta_dev, p, st)) return rc;
     int rows = 0;
     for (int c = 0; c < nchunk; c++) {
       CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));

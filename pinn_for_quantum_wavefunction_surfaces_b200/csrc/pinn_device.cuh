@@ -171,6 +171,68 @@ __device__ __forceinline__ void sigm_n(const float (&u)[N], float (&s)[N]) {
   for (int i = 0; i < N; i++) s[i] = rcp_approx(e[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// theta (1521 scalars, state_dict order) -> the weight image the kernels read (Wts).  Run by `nt` threads (t = 0..nt-1):
+// by prep_weights_kernel into global memory for the FFMA engine (FULL = true: also the plain mat-vec rows), and by every
+// CTA of the tcgen05 kernel straight into its shared memory (FULL = false: only what lies in front of Wts::W2).
+// ---------------------------------------------------------------------------------------------
+template <bool FULL>
+__device__ __forceinline__ void build_weight_image(const float* __restrict__ th, Wts* __restrict__ out, int t, int nt) {
+  for (int i = t; i < NH; i += nt) {
+    const float a = th[O_W1 + 2 * i], b = th[O_W1 + 2 * i + 1];
+    out->w0[i] = a; out->w1[i] = b; out->b1[i] = th[O_B1 + i];
+    out->ww00[i] = a * a; out->ww01[i] = a * b; out->ww11[i] = b * b;
+    out->b2[i] = th[O_B2 + i]; out->wo[i] = th[O_WO + i];
+  }
+  for (int i = t; i < NE; i += nt) {
+    out->WE1[i] = th[O_WE1 + i]; out->bE1[i] = th[O_BE1 + i];
+    out->bE2[i] = th[O_BE2 + i]; out->wE[i] = th[O_WE + i];
+  }
+  for (int i = t; i < 12; i += nt) {
+    const bool in = i < NL;
+    out->WgL[i] = in ? th[O_WGL + i] : 0.0f;
+    out->bgL[i] = in ? th[O_BGL + i] : 0.0f;
+    out->wg[i] = in ? th[O_WG + i] : 0.0f;
+  }
+  if (t == 0) { out->bo = th[O_BO]; out->bE = th[O_BE]; out->bg = th[O_BG]; out->pad0 = 0.0f; }
+  if (FULL) {
+    for (int i = t; i < NH * NH; i += nt) {
+      const int j = i / NH, k = i % NH;
+      out->W2[i] = th[O_W2 + i];
+      out->W2T[k * NH + j] = th[O_W2 + i];
+    }
+    for (int i = t; i < NE * NE; i += nt) {
+      const int j = i / NE, k = i % NE;
+      out->WE2[i] = th[O_WE2 + i];
+      out->WE2T[k * NE + j] = th[O_WE2 + i];
+    }
+  }
+  // ---- tcgen05 operand images: value -> (hi, lo) TF32 pair, round-to-nearest split ----
+  auto put = [](float* hi, float* lo, int off, float v) {
+    uint32_t h, l;
+    split_tf32_rn(v, h, l);
+    hi[off] = __uint_as_float(h);
+    lo[off] = __uint_as_float(l);
+  };
+  for (int i = t; i < NH * NH; i += nt) {
+    const int j = i / NH, k = i % NH;
+    const float wjk = th[O_W2 + i];
+    const float a = th[O_W1 + 2 * k], b = th[O_W1 + 2 * k + 1];
+    put(out->BS[0], out->BS[1], umma_off(j, k, NH), wjk);
+    put(out->BSP[0], out->BSP[1], umma_off(j, k, 2 * NH), wjk * a);
+    put(out->BSP[0], out->BSP[1], umma_off(NH + j, k, 2 * NH), wjk * b);
+    put(out->BSPP[0], out->BSPP[1], umma_off(j, k, 3 * NH), wjk * (a * a));
+    put(out->BSPP[0], out->BSPP[1], umma_off(NH + j, k, 3 * NH), wjk * (a * b));
+    put(out->BSPP[0], out->BSPP[1], umma_off(2 * NH + j, k, 3 * NH), wjk * (b * b));
+    put(out->BWT[0], out->BWT[1], umma_off(k, j, NH), wjk);
+  }
+  for (int i = t; i < NE * NE; i += nt) {
+    const int j = i / NE, k = i % NE;
+    put(out->BE[0], out->BE[1], umma_off(j, k, NE), th[O_WE2 + i]);
+    put(out->BET[0], out->BET[1], umma_off(k, j, NE), th[O_WE2 + i]);
+  }
+}
+
 #define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
 #define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))
 

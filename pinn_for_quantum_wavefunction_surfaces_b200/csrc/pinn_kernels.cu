@@ -647,58 +647,7 @@ __global__ void __launch_bounds__((NEV + 1) * 32 * G, 1) pinn_step_kernel(const 
 // theta -> Wts image
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_weights_kernel(const float* __restrict__ th, Wts* __restrict__ out) {
-  const int t = threadIdx.x;
-  for (int i = t; i < NH; i += blockDim.x) {
-    const float a = th[O_W1 + 2 * i], b = th[O_W1 + 2 * i + 1];
-    out->w0[i] = a; out->w1[i] = b; out->b1[i] = th[O_B1 + i];
-    out->ww00[i] = a * a; out->ww01[i] = a * b; out->ww11[i] = b * b;
-    out->b2[i] = th[O_B2 + i]; out->wo[i] = th[O_WO + i];
-  }
-  for (int i = t; i < NH * NH; i += blockDim.x) {
-    const int j = i / NH, k = i % NH;
-    out->W2[i] = th[O_W2 + i];
-    out->W2T[k * NH + j] = th[O_W2 + i];
-  }
-  for (int i = t; i < NE; i += blockDim.x) {
-    out->WE1[i] = th[O_WE1 + i]; out->bE1[i] = th[O_BE1 + i];
-    out->bE2[i] = th[O_BE2 + i]; out->wE[i] = th[O_WE + i];
-  }
-  for (int i = t; i < NE * NE; i += blockDim.x) {
-    const int j = i / NE, k = i % NE;
-    out->WE2[i] = th[O_WE2 + i];
-    out->WE2T[k * NE + j] = th[O_WE2 + i];
-  }
-  for (int i = t; i < 12; i += blockDim.x) {
-    const bool in = i < NL;
-    out->WgL[i] = in ? th[O_WGL + i] : 0.0f;
-    out->bgL[i] = in ? th[O_BGL + i] : 0.0f;
-    out->wg[i] = in ? th[O_WG + i] : 0.0f;
-  }
-  if (t == 0) { out->bo = th[O_BO]; out->bE = th[O_BE]; out->bg = th[O_BG]; out->pad0 = 0.0f; }
-  // ---- tcgen05 operand images: value -> (hi, lo) TF32 pair ----
-  auto put = [](float* hi, float* lo, int off, float v) {
-    uint32_t h, l;
-    split_tf32_rn(v, h, l);  // round-to-nearest split, see pinn_device.cuh
-    hi[off] = __uint_as_float(h);
-    lo[off] = __uint_as_float(l);
-  };
-  for (int i = t; i < NH * NH; i += blockDim.x) {
-    const int j = i / NH, k = i % NH;
-    const float wjk = th[O_W2 + i];
-    const float a = th[O_W1 + 2 * k], b = th[O_W1 + 2 * k + 1];
-    put(out->BS[0], out->BS[1], umma_off(j, k, NH), wjk);
-    put(out->BSP[0], out->BSP[1], umma_off(j, k, 2 * NH), wjk * a);
-    put(out->BSP[0], out->BSP[1], umma_off(NH + j, k, 2 * NH), wjk * b);
-    put(out->BSPP[0], out->BSPP[1], umma_off(j, k, 3 * NH), wjk * (a * a));
-    put(out->BSPP[0], out->BSPP[1], umma_off(NH + j, k, 3 * NH), wjk * (a * b));
-    put(out->BSPP[0], out->BSPP[1], umma_off(2 * NH + j, k, 3 * NH), wjk * (b * b));
-    put(out->BWT[0], out->BWT[1], umma_off(k, j, NH), wjk);
-  }
-  for (int i = t; i < NE * NE; i += blockDim.x) {
-    const int j = i / NE, k = i % NE;
-    put(out->BE[0], out->BE[1], umma_off(j, k, NE), th[O_WE2 + i]);
-    put(out->BET[0], out->BET[1], umma_off(k, j, NE), th[O_WE2 + i]);
-  }
+  build_weight_image<true>(th, out, threadIdx.x, blockDim.x);
 }
 
 // counts of the two boundary sets -> weights {1/n, 1/cnt1, 1/cnt2} (only when the caller passes no weights)

@@ -22,7 +22,8 @@ struct GridDesc {
 struct StepParams {
   const void *x, *y, *z, *R;
   const uint8_t* mask;
-  const Wts* wts;
+  const Wts* wts;         // FFMA engine: weight image built by prep_weights_kernel
+  const float* theta;     // tcgen05 engine: the raw parameter vector; every CTA builds its own image in shared memory
   const double* weights;  // {w_pde, w_bc1, w_bc2}
   double* partials;       // [gridDim.x][NPART]
   float* E_out;

@@ -110,41 +110,22 @@ template <bool STASH>
 __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t cb, float a, float b, float al1, float al2,
                                                float al11, float al12, float al22, float* __restrict__ Hrow,
                                                float* __restrict__ Grow, int sx, float& Nv, float& Dv) {
-  {
-    float s_[NH], sp_[NH], spp_[NH];
+  float s_[NH], sp_[NH], spp_[NH];
 #pragma unroll
-    for (int k4 = 0; k4 < NH; k4 += 4) {
-      const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]), b1v = LD4(&w.b1[k4]);
-      const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
-      const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
+  for (int k4 = 0; k4 < NH; k4 += 4) {
+    const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]), b1v = LD4(&w.b1[k4]);
+    const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+    const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const float u = fmaf(a, w0a[i], fmaf(b, w1a[i], b1a[i]));
-        const float s = sigm(u);
-        const float sp = fmaf(-s, s, s);            // s(1-s)
-        const float spp = fmaf(-2.0f * s, sp, sp);  // s'(1-2s)
-        s_[k4 + i] = s; sp_[k4 + i] = sp; spp_[k4 + i] = spp;
-      }
-      if (STASH) {
-        // the 4-channel h of the weight-gradient contraction and of the reverse sweep
-        const float4 q00 = LD4(&w.ww00[k4]), q01 = LD4(&w.ww01[k4]), q11 = LD4(&w.ww11[k4]);
-        const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
-        const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
-        float h1[4], h2[4], h3[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float d1 = fmaf(al1, w0a[i], al2 * w1a[i]);
-          const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
-          h1[i] = sp_[k4 + i] * w0a[i];
-          h2[i] = sp_[k4 + i] * w1a[i];
-          h3[i] = fmaf(sp_[k4 + i], d1, spp_[k4 + i] * q);
-        }
-        ST4(&Hrow[(0 * NH + k4) ^ sx], s_[k4], s_[k4 + 1], s_[k4 + 2], s_[k4 + 3]);
-        ST4(&Hrow[(1 * NH + k4) ^ sx], h1[0], h1[1], h1[2], h1[3]);
-        ST4(&Hrow[(2 * NH + k4) ^ sx], h2[0], h2[1], h2[2], h2[3]);
-        ST4(&Hrow[(3 * NH + k4) ^ sx], h3[0], h3[1], h3[2], h3[3]);
-      }
+    for (int i = 0; i < 4; i++) {
+      const float u = fmaf(a, w0a[i], fmaf(b, w1a[i], b1a[i]));
+      const float s = sigm(u);
+      const float sp = fmaf(-s, s, s);            // s(1-s)
+      const float spp = fmaf(-2.0f * s, sp, sp);  // s'(1-2s)
+      s_[k4 + i] = s; sp_[k4 + i] = sp; spp_[k4 + i] = spp;
     }
+  }
+  {
     const uint32_t t0 = c.tlane + cb;
     tc_st_split16<true>(t0 + F_S_HI, t0 + F_S_LO, s_);
     tc_st_split16<true>(t0 + F_SP_HI, t0 + F_SP_LO, sp_);
@@ -171,6 +152,30 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
     tc_commit(c.mbar);
   }
   __syncwarp();
+  if (STASH) {
+    // while the tensor pipe works: the 4-channel h of the weight-gradient contraction and of the reverse sweep
+#pragma unroll
+    for (int k4 = 0; k4 < NH; k4 += 4) {
+      const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]);
+      const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
+      const float4 q00 = LD4(&w.ww00[k4]), q01 = LD4(&w.ww01[k4]), q11 = LD4(&w.ww11[k4]);
+      const float q00a[4] = {q00.x, q00.y, q00.z, q00.w}, q01a[4] = {q01.x, q01.y, q01.z, q01.w};
+      const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
+      float h1[4], h2[4], h3[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float d1 = fmaf(al1, w0a[i], al2 * w1a[i]);
+        const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
+        h1[i] = sp_[k4 + i] * w0a[i];
+        h2[i] = sp_[k4 + i] * w1a[i];
+        h3[i] = fmaf(sp_[k4 + i], d1, spp_[k4 + i] * q);
+      }
+      ST4(&Hrow[(0 * NH + k4) ^ sx], s_[k4], s_[k4 + 1], s_[k4 + 2], s_[k4 + 3]);
+      ST4(&Hrow[(1 * NH + k4) ^ sx], h1[0], h1[1], h1[2], h1[3]);
+      ST4(&Hrow[(2 * NH + k4) ^ sx], h2[0], h2[1], h2[2], h2[3]);
+      ST4(&Hrow[(3 * NH + k4) ^ sx], h3[0], h3[1], h3[2], h3[3]);
+    }
+  }
   tc_wait_mma(c);
   TL(3);
 
@@ -607,16 +612,40 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 32) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbars[0])),
-                 "r"((uint32_t)WTS_TC_BYTES)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&w)),
-        "l"(p.wts), "r"((uint32_t)WTS_TC_BYTES), "r"(smem_u32(&mbars[0]))
-        : "memory");
+  const int slot = grp * 32 + lane;
+  const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
+  if (stager) {
+    const long long i0 = (long long)blockIdx.x * 128 + slot;
+    coord_stage_issue(p, cstage, slot, i0 < p.n ? i0 : p.n - 1);
+    cp_async_commit();
   }
-  mbar_wait(smem_u32(&mbars[0]), 0);
+
+  // ---- weights: theta arrives in shared memory by ONE TMA bulk copy (6080 of its 6084 bytes; bulk copies move multiples
+  //      of 16 bytes), every thread then takes part in turning it into the image the kernel reads: layer-1 rows, the
+  //      pre-multiplied and hi/lo-split tensor-core operands in the canonical K-major layout.  No separate prep launch.
+  {
+    float* th_s = stash;  // the stash is free until the first super-tile
+    constexpr uint32_t TH_BULK = (NTHETA * 4 / 16) * 16;
+    const bool bulk_ok = ((uintptr_t)p.theta & 15u) == 0;
+    if (bulk_ok) {
+      if (tid == 32) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbars[0])), "r"(TH_BULK) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(th_s)),
+            "l"(p.theta), "r"(TH_BULK), "r"(smem_u32(&mbars[0]))
+            : "memory");
+      }
+      for (int i = TH_BULK / 4 + tid; i < NTHETA; i += blockDim.x) th_s[i] = p.theta[i];
+      mbar_wait(smem_u32(&mbars[0]), 0);
+    } else {  // unaligned caller buffer: plain loads
+      for (int i = tid; i < NTHETA; i += blockDim.x) th_s[i] = p.theta[i];
+    }
+    __syncthreads();
+    build_weight_image<false>(th_s, &w, tid, blockDim.x);
+    // the tensor cores read the operand images through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
 
   TcCtx c;
   c.tbase = *tmem_slot;
@@ -653,14 +682,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   // 32 points lie beyond n compute on a clamped index with zero weight
   const long long nsuper = (p.n + 127) >> 7;
   int it = 0;
-  const int slot = grp * 32 + lane;
-  const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
-  if (stager) {
-    const long long i0 = (long long)blockIdx.x * 128 + slot;
-    coord_stage_issue(p, cstage, slot, i0 < p.n ? i0 : p.n - 1);
-    cp_async_commit();
-    cp_async_wait_all();
-  }
+  if (stager) cp_async_wait_all();  // the first super-tile's coordinates (requested before the weight image was built)
   __syncthreads();
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
     const long long pidx = st * 128 + slot;

@@ -133,7 +133,7 @@ int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, in
   CU(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   p.n = (long long)nx * ny * nz;
-  p.wts = h->wts;
+  p.theta = theta;
   p.grid.on = 1; p.grid.nx = nx; p.grid.ny = ny; p.grid.nz = nz;
   p.grid.x0 = lim[0]; p.grid.dx = (lim[1] - lim[0]) / (nx - 1);
   p.grid.y0 = lim[2]; p.grid.dy = (lim[3] - lim[2]) / (ny - 1);
@@ -141,10 +141,9 @@ int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, in
   p.grid.R = R; p.grid.wx = wx; p.grid.wy = wy; p.grid.wz = wz; p.grid.partials = h->grid_partials;
   const long long tiles = (p.n + 127) / 128;
   const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  CU(h, launch_prep(theta, h->wts, st));
   CU(h, launch_step_tc(nev, false, p, grid, st));  // the dense-grid mode lives in the tcgen05 kernel
   CU(h, launch_grid_finish(h->grid_partials, grid, out, st));
-  h->launches += 3;
+  h->launches += 2;
   return 0;
 }
 
