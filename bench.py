@@ -103,6 +103,54 @@ def cpu_reference_points_per_s(theta, min_seconds, max_points=1 << 16, threads=N
     return max_points / best, cores, "%d points x %d evaluations (best of), float64 nested autograd" % (max_points, len(times)), best
 
 
+def ref_autograd_on_gpu(theta, dev, n=1 << 18):
+    """BASELINE config 2: the reference's own algorithm (nested torch autograd, oracle/ref_autograd.py) executed by
+    PyTorch on the same B200, float64 as shipped and float32, on one 2^18-point batch."""
+    import torch
+    from oracle import ref_autograd as ra
+    g = torch.Generator().manual_seed(4321)
+    x, y, z, R, i1, i2 = ra.sample_box(n, "poc", g)
+    out = {}
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        a = [t.to(device=dev, dtype=dt) for t in (x, y, z, R)]
+        j1, j2 = i1.to(dev), i2.to(dev)
+        th = torch.tensor(theta, dtype=dt, device=dev)
+        for _ in range(2):
+            ra.loss_and_grad("poc", th, *a, j1, j2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            ra.loss_and_grad("poc", th, *a, j1, j2)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"value": n / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms}
+    out["what"] = "torch eager nested autograd of the reference model on cuda:0, %d points, %d evaluations each" % (n, reps)
+    return out
+
+
+def dense_grid_inference(dev, n_axis=464):
+    """BASELINE config 5: psi, H psi and the Simpson-weighted energy sums on a 464^3 = 1.0e8-point grid at one R
+    (models/ionHsym_fineTune.pt weights), points generated in-kernel, only 5 sums leave each SM."""
+    import torch
+    import pinn_for_quantum_wavefunction_surfaces_b200 as pk
+    th = np.load(os.path.join(ROOT, "tests", "golden", "checkpoints.npz"))["ionHsym_fineTune"]
+    pk.analysis.grid_sums(th, 2.0, n=80, device=dev.index)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = pk.analysis.grid_sums(th, 2.0, n=n_axis, device=dev.index)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    pts = float(n_axis) ** 3
+    # fixed-R inference: 6 656 FLOP/point (SURVEY.md 8d)
+    return {"value": pts / (ms * 1e-3), "unit": "points/s", "ms": ms, "grid": "%d^3" % n_axis,
+            "E_int": r["psiHpsi"] / r["psi2"], "frac_of_fp32_peak": 6656.0 * pts / (ms * 1e-3) / FP32_PEAK_MEASURED}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -282,6 +330,12 @@ def main():
                 "what": "pinn_trainer: Philox sampler + fused loss/gradient + float64 Adam per step, one CUDA-graph replay each, no host sync"}
         tr.close()
 
+    # ---- two more reference points for N = 1 (BASELINE configs 2 and 5) ----
+    extra = {}
+    if world == 1 and not args.no_cpu_baseline:
+        extra["reference_autograd_on_gpu"] = ref_autograd_on_gpu(load_theta(), dev)
+        extra["dense_grid_inference"] = dense_grid_inference(dev)
+
     if rank == 0:
         total_points = float(n) * world
         value = total_points * K / (ms * 1e-3)
@@ -316,6 +370,7 @@ def main():
         }
         if loop:
             line["device_train_loop"] = loop
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}

@@ -30,8 +30,13 @@
 __device__ long long g_timeline[16 * 32];
 #define TL(i) do { if (blockIdx.x == 0 && c.tl_it == 3 && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 32 + (i)] = clock64(); } while (0)
 extern "C" int pinn_debug_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)); }
+// whole-kernel stamps of warp 0 of CTA 0: [0] entry, [1] setup done, [2 + it] start of its it-th super-tile, [40] loop done, [41] end
+__device__ long long g_timeline_k[48];
+#define TLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_timeline_k[(i)] = clock64(); } while (0)
+extern "C" int pinn_debug_timeline_kernel(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_timeline_k, sizeof(g_timeline_k)); }
 #else
 #define TL(i) do { } while (0)
+#define TLK(i) do { } while (0)
 #endif
 
 namespace pinn {
@@ -598,6 +603,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   const int role = warp >> 2, grp = warp & 3;
   const bool is_mlp = role < NEV;
   const int sx = swz(lane);
+  TLK(0);
 
   // ---- one-time setup: TMEM allocation (warp 0), mbarriers, weight image by TMA bulk copy ----
   if (warp == 0) {
@@ -684,12 +690,14 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   int it = 0;
   if (stager) cp_async_wait_all();  // the first super-tile's coordinates (requested before the weight image was built)
   __syncthreads();
+  TLK(1);
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
     const long long pidx = st * 128 + slot;
     const bool valid = pidx < p.n;
     const long long pi = valid ? pidx : (p.n - 1);
     c.tl_it = it;
     TL(0);
+    if (it < 38) TLK(2 + it);
     const unsigned char* cbuf = cstage + (it & 1) * COORD_STAGE_BYTES;
     const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
     const Geom g = geom_from_raw(raw);
@@ -814,6 +822,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     TL(15);
   }
 
+  TLK(40);
   // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
   tc_fence_before();
   __syncthreads();
@@ -892,6 +901,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     for (int wv = 0; wv < nwarps; wv++) sum += (double)stash[wv * NPART + i];
     row[i] = sum;
   }
+  TLK(41);
 }
 
 // =================================================================================================

@@ -45,3 +45,9 @@ for wv in range(nw):
     row = tl[wv]
     print("%4d %4d %3d | " % (wv, role, grp) + " ".join("%6d" % (row[k] - t0 if row[k] else -1) for k in sorted(names)))
 print("tile length (warp 0): %d cycles" % (tl[0, 15] - tl[0, 0]))
+
+kb = (ctypes.c_longlong * 48)()
+assert h.L.pinn_debug_timeline_kernel(kb) == 0
+k = np.array(kb[:])
+print("CTA 0, warp 0: setup %d cycles | first tiles %s | steady tile %d | epilogue (fold) %d cycles | kernel body %d cycles = %.1f us" % (
+    k[1] - k[0], " ".join(str(int(k[3 + i] - k[2 + i])) for i in range(6)), k[10] - k[9], k[41] - k[40], k[41] - k[0], (k[41] - k[0]) / 1965.0))
