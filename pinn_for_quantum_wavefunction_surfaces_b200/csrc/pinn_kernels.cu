@@ -674,7 +674,8 @@ __global__ void weights_from_counts_kernel(const unsigned long long* counts, lon
 
 // ---------------------------------------------------------------------------------------------
 // add the partial rows (fixed order, double) -> dtheta, sums
-// block = 256 threads = 32 entries x 8 row-slices
+// block = 1024 threads = 32 entries x 32 row-slices (every thread has at most 5 independent loads in flight: one
+// round trip to L2 instead of a chain of 19)
 //
 // With dp.world > 1 the kernel is also the data-parallel all-reduce, in the style of a low-latency (LL) protocol: every
 // float64 travels as two 8-byte words {32 data bits, 32-bit step number}; 8-byte stores are single-copy atomic, so a
@@ -684,6 +685,8 @@ __global__ void weights_from_counts_kernel(const unsigned long long* counts, lon
 // computes bit-identical sums.  No NCCL launch, no extra kernel.  Two slots alternate by step parity: a peer can be at
 // most one exchange ahead (it needs this rank's next contribution to go further).
 // ---------------------------------------------------------------------------------------------
+constexpr int RED_SLICES = 32;
+static_assert(RED_SLICES >= DP_MAX_WORLD, "one row-slice of threads per data-parallel peer");
 __device__ __forceinline__ void st_relaxed_sys_v2(unsigned int* p, unsigned int a, unsigned int b) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
@@ -701,16 +704,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
+__global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
                                                               const double* __restrict__ weights, uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
                                                               const float* __restrict__ E_out, long long n, const DpArgs dp) {
-  __shared__ double sh[8][33];
+  __shared__ double sh[RED_SLICES][33];
   __shared__ double tot[32];
   const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + e;
   double s = 0.0;
-  for (int r = sl; r < nrows; r += 8) s += partials[(size_t)r * NPART + idx];
+#pragma unroll 5
+  for (int r = sl; r < nrows; r += RED_SLICES) s += partials[(size_t)r * NPART + idx];
   sh[sl][e] = s;
   __syncthreads();
   if (dp.world > 1) {
@@ -722,7 +726,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     if (sl == 0) {
       double t = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; i++) t += sh[i][e];
+      for (int i = 0; i < RED_SLICES; i++) t += sh[i][e];
       tot[e] = t;
     }
     __syncthreads();
@@ -765,7 +769,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   if (sl == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) t += sh[i][e];
+    for (int i = 0; i < RED_SLICES; i++) t += sh[i][e];
     tot[e] = t;
     if (idx < NTHETA) {
       // tensor index of this scalar -> honour grad_mask
@@ -834,7 +838,7 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
                           double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st) {
-  reduce_partials_kernel<<<DP_BLOCKS, 256, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
+  reduce_partials_kernel<<<DP_BLOCKS, RED_SLICES * 32, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
   return cudaGetLastError();
 }
 
