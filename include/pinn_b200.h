@@ -152,6 +152,11 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n,
  *                         transport, e.g. torch.distributed)       ->  pinn_dp_connect(h, all_handles)
  *   one process, several handles/devices:  pinn_dp_init(h_r, r, world, NULL) for all r, then
  *                         pinn_dp_connect_local(h_r, handles) for all r
+ * The device-resident trainer (pinn_trainer_*) created on a handle with the exchange enabled runs data-parallel without
+ * any host involvement: rank r draws points [r n, (r+1) n) of the global batch (Philox counter = global point index, so
+ * the union over the ranks is the batch one GPU would draw for world*n points), the sampler's set sizes are summed
+ * over the ranks with the same protocol, and every rank's Adam sees the same global gradient (identical replicas).
+ * Connect the exchange BEFORE creating the trainer (the peers' addresses are captured in its CUDA graphs).
  * pinn_dp_connect* enable the exchange; pinn_dp_enable switches it off/on; pinn_dp_status returns PINN_ETIMEDOUT if a
  * peer failed to deliver within ~3 s (the kernel then gives up instead of hanging) and the number of completed
  * exchanges; pinn_dp_shutdown (collective by convention: call it on every rank after a barrier) frees the buffer.

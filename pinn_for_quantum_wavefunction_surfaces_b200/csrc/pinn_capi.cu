@@ -34,7 +34,7 @@ int pinn_create(int device, pinn_handle** out) {
   CU(nullptr, cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(nullptr, PINN_ENOTSUP, "pinn_create: this library only carries sm_100a code (B200); no fallback exists");
-  CU(nullptr, cudaSetDevice(device));
+  DevGuard dev_guard(device);
   pinn_handle* h = new pinn_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
@@ -78,7 +78,7 @@ static void dp_release(pinn_handle* h) {
 
 int pinn_destroy(pinn_handle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DevGuard dev_guard(h->device);
   dp_release(h);
   cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->counts);
   cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
@@ -115,7 +115,7 @@ int pinn_profile_begin(pinn_handle* h) {
 int pinn_profile_collect(pinn_handle* h, double* total_ms, int* launches) {
   if (!h || !total_ms || !launches) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   double tot = 0.0;
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     CU(h, cudaEventSynchronize(h->ev_pool[i + 1]));
@@ -147,7 +147,7 @@ int pinn_dp_init(pinn_handle* h, int rank, int world, void* ipc_handle_out) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world)
     return fail(h, PINN_EINVAL, "pinn_dp_init: need 0 <= rank < world <= 8");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   dp_release(h);
   CU(h, cudaMalloc(&h->dp_buf, DP_BUFFER_BYTES));
   CU(h, cudaMemset(h->dp_buf, 0, DP_BUFFER_BYTES));
@@ -168,7 +168,7 @@ int pinn_dp_connect(pinn_handle* h, const void* all_handles) {
   if (!h || !all_handles) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_connect: call pinn_dp_init first");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   for (int r = 0; r < h->dp.world; r++) {
     if (r == h->dp.rank) continue;
     cudaIpcMemHandle_t ih;
@@ -186,7 +186,7 @@ int pinn_dp_connect_local(pinn_handle* h, pinn_handle* const* peers) {
   if (!h || !peers) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_connect_local: call pinn_dp_init first");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   for (int r = 0; r < h->dp.world; r++) {
     if (r == h->dp.rank) continue;
     pinn_handle* q = peers[r];
@@ -222,7 +222,7 @@ int pinn_dp_status(pinn_handle* h, int64_t* exchanges) {
   if (!h) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->dp_buf) return fail(h, PINN_EINVAL, "pinn_dp_status: the exchange is not initialised");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   unsigned long long ctl[3];
   CU(h, cudaMemcpy(ctl, h->dp_buf + DP_ROWS_BYTES, sizeof(ctl), cudaMemcpyDeviceToHost));
   if (exchanges) *exchanges = (int64_t)ctl[0];
@@ -233,7 +233,7 @@ int pinn_dp_status(pinn_handle* h, int64_t* exchanges) {
 int pinn_dp_shutdown(pinn_handle* h) {
   if (!h) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   CU(h, cudaDeviceSynchronize());
   dp_release(h);
   return 0;
@@ -309,7 +309,7 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
   if (!x || !y || !z || !R || !theta || !sums || !dtheta)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.bcut = bcutoff; p.partials = h->partials; p.E_out = E_out;
@@ -341,7 +341,7 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const voi
   if (n <= 0) return fail(h, PINN_EINVAL, "pinn_fields: n must be positive");
   if (!x || !y || !z || !R || !theta) return fail(h, PINN_EINVAL, "pinn_fields: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_fields: bad in_dtype");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   p.x = x; p.y = y; p.z = z; p.R = R; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.psi = psi; p.lap = lap; p.hpsi = hpsi; p.res = res; p.E_out = E;
@@ -361,7 +361,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: bad in_dtype");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   const size_t es = in_dtype == PINN_F64 ? 8 : 4;
   // Page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) inputs are read by the kernel in place: the
   // step kernel requests the coordinates of its next super-tile one tile ahead, which hides the PCIe latency, and

@@ -47,6 +47,20 @@ struct pinn_handle {
   std::mutex mu;
 };
 
+// Every entry point works on the handle's device and leaves the caller's current device as it found it.
+struct DevGuard {
+  int prev = -1, dev;
+  explicit DevGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DevGuard(const DevGuard&) = delete;
+  DevGuard& operator=(const DevGuard&) = delete;
+};
+
 extern std::string g_create_err;
 
 inline int fail(pinn_handle* h, int code, const char* what) {

@@ -47,11 +47,14 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 // peers of the box can write through NVLink peer memory (cudaIpc / peer access).
 //   rows [2 slots][DP_MAX_WORLD][NPART] x 16 B : rank r deposits its reduced row in slot (step & 1), index r, of EVERY
 //        rank; each float64 is two 8-byte words {32 data bits, 32-bit step number} (pinn_kernels.cu: reduce_partials_kernel)
-//   ctl  {exchanges completed, blocks done, status}
+//   ctl  8 x u64 {exchanges completed, blocks done, status, set-count exchanges completed, ...}
+//   cnt  [2 slots][DP_MAX_WORLD][2] x 8 B : the sampler's boundary-set sizes, same {data, step} words (pinn_train.cu)
 constexpr int DP_MAX_WORLD = 8;
 constexpr int DP_BLOCKS = NPART / 32;
 constexpr size_t DP_ROWS_BYTES = 2ull * DP_MAX_WORLD * NPART * 16;
-constexpr size_t DP_BUFFER_BYTES = DP_ROWS_BYTES + 64;
+constexpr size_t DP_CTL_BYTES = 64;
+constexpr size_t DP_CNT_BYTES = 2ull * DP_MAX_WORLD * 2 * 8;
+constexpr size_t DP_BUFFER_BYTES = DP_ROWS_BYTES + DP_CTL_BYTES + DP_CNT_BYTES;
 struct DpArgs {
   int world = 0;  // <= 1: no exchange
   int rank = 0;

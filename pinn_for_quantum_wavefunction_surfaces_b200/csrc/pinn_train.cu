@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
   unsigned c1 = 0, c2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)batch, (uint32_t)(batch >> 32),
+    const unsigned long long gi = (unsigned long long)(i + s.index_offset);  // index of the point in the global batch
+    philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)batch, (uint32_t)(batch >> 32),
                   (uint32_t)s.seed, (uint32_t)(s.seed >> 32), r);
     float x = fmaf(s.xR - s.xL, u01(r[0]), s.xL);
     const float y = fmaf(s.yR - s.yL, u01(r[1]), s.yL);
@@ -67,21 +68,64 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
 }
 
 // weights {1/n, 1/|set1|, 1/|set2|} of the reference's means (empty set -> inf -> NaN loss, as in the reference),
-// and the batch counter moves on
-__global__ void sample_finish_kernel(const unsigned long long* counts, long long n, double* w, unsigned long long* batch_counter) {
-  w[0] = 1.0 / (double)n;
-  w[1] = 1.0 / (double)counts[0];
-  w[2] = 1.0 / (double)counts[1];
-  *batch_counter += 1ull;
+// and the batch counter moves on.  One warp.  Data-parallel runs (dp.world > 1) first add the set sizes of all ranks:
+// lane r stores this rank's two counts into peer r's exchange buffer as {count, step} words and polls its own buffer
+// for peer r's (same protocol as the gradient sum in reduce_partials_kernel), lane 0 adds them in rank order.
+__global__ void sample_finish_kernel(const unsigned long long* counts, long long n, double* w, unsigned long long* batch_counter,
+                                     const DpArgs dp) {
+  __shared__ unsigned long long c[DP_MAX_WORLD][2];
+  const int lane = threadIdx.x;
+  unsigned long long c1 = counts[0], c2 = counts[1];
+  long long ntot = n;
+  if (dp.world > 1) {
+    unsigned char* own = dp.peer[dp.rank];
+    unsigned long long* ctl = reinterpret_cast<unsigned long long*>(own + DP_ROWS_BYTES);
+    const unsigned long long step64 = ld_acquire_sys(&ctl[3]) + 1;
+    const unsigned int step = (unsigned int)step64;
+    const size_t slot = (size_t)(step64 & 1ull) * DP_MAX_WORLD;
+    if (lane < dp.world) {
+      const int r = lane;
+      if (r == dp.rank) {
+        c[r][0] = c1; c[r][1] = c2;
+      } else {
+        unsigned int* dst = reinterpret_cast<unsigned int*>(dp.peer[r] + DP_ROWS_BYTES + DP_CTL_BYTES) + (slot + dp.rank) * 4;
+        st_relaxed_sys_v2(dst, (unsigned int)c1, step);
+        st_relaxed_sys_v2(dst + 2, (unsigned int)c2, step);
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(own + DP_ROWS_BYTES + DP_CTL_BYTES) + (slot + r) * 4;
+        const long long t0 = clock64();
+        uint2 a, b;
+        for (;;) {
+          a = ld_relaxed_sys_v2(src);
+          b = ld_relaxed_sys_v2(src + 2);
+          if (a.y == step && b.y == step) break;
+          if (clock64() - t0 > 6000000000ll) { ctl[2] = 1ull; break; }
+        }
+        c[r][0] = a.x; c[r][1] = b.x;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      c1 = 0; c2 = 0;
+      for (int r = 0; r < dp.world; r++) { c1 += c[r][0]; c2 += c[r][1]; }
+      ntot = n * dp.world;
+      st_release_sys(&ctl[3], step64);
+    }
+  }
+  if (lane == 0) {
+    w[0] = 1.0 / (double)ntot;
+    w[1] = 1.0 / (double)c1;
+    w[2] = 1.0 / (double)c2;
+    *batch_counter += 1ull;
+  }
 }
 
-cudaError_t launch_sample(const SampleParams& s, double* weights, cudaStream_t st) {
+cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& dp, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(s.counts, 0, 2 * sizeof(unsigned long long), st);
   if (e != cudaSuccess) return e;
   long long blocks = (s.n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   sample_kernel<<<(int)blocks, 256, 0, st>>>(s);
-  sample_finish_kernel<<<1, 1, 0, st>>>(s.counts, s.n, weights, s.batch_counter);
+  sample_finish_kernel<<<1, 32, 0, st>>>(s.counts, s.n, weights, s.batch_counter, dp);
   return cudaGetLastError();
 }
 

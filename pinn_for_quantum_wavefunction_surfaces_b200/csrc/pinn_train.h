@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pinn_launch.h"
+
 namespace pinn {
 
 struct SampleParams {
@@ -14,6 +16,7 @@ struct SampleParams {
   float *x, *y, *z, *R;
   uint8_t* mask;
   unsigned long long* counts;  // device, 2: sizes of the two boundary sets
+  long long index_offset;      // data-parallel shard: this rank draws points [index_offset, index_offset + n) of the batch
 };
 
 struct AdamParams {
@@ -31,7 +34,9 @@ struct AdamParams {
   int best_mode, hist_mean_E;
 };
 
-cudaError_t launch_sample(const SampleParams& s, double* weights, cudaStream_t st);
+// dp.world > 1: the set sizes are summed over the ranks (same exchange buffers as the gradient sum) and weights become
+// {1/(world*n), 1/|set1|, 1/|set2|} of the GLOBAL batch
+cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& dp, cudaStream_t st);
 cudaError_t launch_adam(const AdamParams& a, cudaStream_t st);
 cudaError_t launch_enet_curve(const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
                               cudaStream_t st);

@@ -35,7 +35,11 @@ static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
     s.xL = c.xL; s.xR = c.xR; s.yL = c.yL; s.yR = c.yR; s.zL = c.zL; s.zR = c.zR; s.RL = c.RL; s.RR = c.RR;
     s.cutoff = c.cutoff; s.bcutoff = c.bcutoff;
     s.x = t->x; s.y = t->y; s.z = t->z; s.R = t->R; s.mask = t->mask; s.counts = t->counts;
-    CU(h, launch_sample(s, t->weights, st));
+    // data-parallel: rank r draws points [r n, (r+1) n) of the global batch of world*n points, so the union over the
+    // ranks is exactly the batch a single GPU would draw for n_global = world*n
+    const bool dp_run = h->dp_on && h->dp.world > 1;
+    s.index_offset = dp_run ? (long long)h->dp.rank * c.n : 0;
+    CU(h, launch_sample(s, t->weights, dp_run ? h->dp : DpArgs(), st));
     h->launches += 2;
   }
   int rc = pinn_loss_fwd_bwd(h, c.variant, c.n, t->x, t->y, t->z, t->R, PINN_F32, t->mask, t->theta32, t->weights,
@@ -44,7 +48,8 @@ static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
   AdamParams a{};
   a.theta = t->theta; a.m = t->m; a.v = t->v; a.grad = t->grad; a.sums = t->sums; a.theta32 = t->theta32;
   a.step = t->step; a.best_loss = t->best_loss; a.best_theta = t->best_theta; a.best_step = t->best_step;
-  a.hist = t->hist; a.hist_cap = c.history_capacity; a.n = c.n;
+  a.hist = t->hist; a.hist_cap = c.history_capacity;
+  a.n = c.n * ((h->dp_on && h->dp.world > 1) ? h->dp.world : 1);  // mean E of the history is over the global batch
   a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.eps; a.best_after = (double)c.best_after;
   a.grad_mask = c.grad_mask; a.best_mode = c.best_mode; a.hist_mean_E = c.history_mean_E;
   CU(h, launch_adam(a, st));
@@ -76,7 +81,7 @@ int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const 
   std::lock_guard<std::mutex> lk(h->mu);
   if (n <= 0 || !box || !x || !y || !z || !R || !mask || !counts || !weights)
     return fail(h, PINN_EINVAL, "pinn_sample: bad argument");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   set_u64_kernel<<<1, 1, 0, st>>>(h->batch_counter, (unsigned long long)batch);
   SampleParams s{};
@@ -84,7 +89,8 @@ int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const 
   s.xL = box[0]; s.xR = box[1]; s.yL = box[2]; s.yR = box[3]; s.zL = box[4]; s.zR = box[5]; s.RL = box[6]; s.RR = box[7];
   s.cutoff = cutoff; s.bcutoff = bcutoff;
   s.x = x; s.y = y; s.z = z; s.R = R; s.mask = mask; s.counts = (unsigned long long*)counts;
-  CU(h, launch_sample(s, weights, st));
+  s.index_offset = 0;
+  CU(h, launch_sample(s, weights, DpArgs(), st));
   h->launches += 3;
   return 0;
 }
@@ -97,7 +103,7 @@ int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const do
   std::lock_guard<std::mutex> lk(h->mu);
   if (!theta || !m || !v || !grad || !sums || !theta32 || !step || !best_loss || !best_theta || !best_step)
     return fail(h, PINN_EINVAL, "pinn_adam_step: NULL pointer argument");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   AdamParams a{};
   a.theta = theta; a.m = m; a.v = v; a.grad = grad; a.sums = sums; a.theta32 = theta32;
   a.step = (unsigned long long*)step; a.best_loss = best_loss; a.best_theta = best_theta; a.best_step = (long long*)best_step;
@@ -113,7 +119,7 @@ int pinn_enet_curve(pinn_handle* h, const float* theta, const double* R, int n, 
   if (!h) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!theta || !R || n <= 0) return fail(h, PINN_EINVAL, "pinn_enet_curve: bad argument");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   CU(h, launch_enet_curve(theta, R, n, E, dE, d2E, gate, (cudaStream_t)stream));
   h->launches += 1;
   return 0;
@@ -130,7 +136,7 @@ int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, in
   if (variant == PINN_VARIANT_POC) { p.vc = {1.0f, -0.5f, -1.0f, -1.0f}; nev = 2; }
   else if (variant == PINN_VARIANT_TRAINPY) { p.vc = {2.0f, 1.0f, 1.0f, 1.0f}; nev = 1; }
   else return fail(h, PINN_EINVAL, "pinn_grid_reduce: unknown variant");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   p.n = (long long)nx * ny * nz;
   p.theta = theta;
@@ -157,7 +163,7 @@ int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const doub
     return fail(h, PINN_EINVAL, "pinn_trainer_create: n and sc_sampling must be positive");
   if (cfg->variant != PINN_VARIANT_POC && cfg->variant != PINN_VARIANT_TRAINPY)
     return fail(h, PINN_EINVAL, "pinn_trainer_create: unknown variant");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   pinn_trainer* t = new pinn_trainer();
   t->h = h; t->cfg = *cfg;
   *out = nullptr;
@@ -192,7 +198,7 @@ int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const doub
 
 int pinn_trainer_destroy(pinn_trainer* t) {
   if (!t) return 0;
-  cudaSetDevice(t->h->device);
+  DevGuard dev_guard(t->h->device);
   if (t->st) cudaStreamSynchronize(t->st);
   if (t->g_resample) cudaGraphExecDestroy(t->g_resample);
   if (t->g_keep) cudaGraphExecDestroy(t->g_keep);
@@ -210,7 +216,7 @@ int pinn_trainer_load_state(pinn_trainer* t, const double* theta, const double* 
   if (!t) return PINN_EINVAL;
   pinn_handle* h = t->h;
   if (!theta || step < 0) return fail(h, PINN_EINVAL, "pinn_trainer_load_state: bad argument");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   CU(h, cudaStreamSynchronize(t->st));
   CU(h, cudaMemcpy(t->theta, theta, NTHETA * 8, cudaMemcpyHostToDevice));
   float th32[NTHETA];
@@ -231,7 +237,7 @@ int pinn_trainer_set_batch(pinn_trainer* t, const float* x, const float* y, cons
   if (!t) return PINN_EINVAL;
   pinn_handle* h = t->h;
   if (!x || !y || !z || !R || !mask || !weights_host) return fail(h, PINN_EINVAL, "pinn_trainer_set_batch: NULL pointer argument");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   const size_t n = (size_t)t->cfg.n;
   CU(h, cudaMemcpyAsync(t->x, x, n * 4, cudaMemcpyDefault, t->st));
   CU(h, cudaMemcpyAsync(t->y, y, n * 4, cudaMemcpyDefault, t->st));
@@ -252,7 +258,7 @@ int pinn_trainer_run(pinn_trainer* t, int64_t steps, int resample, int use_graph
   pinn_handle* h = t->h;
   if (steps < 0) return fail(h, PINN_EINVAL, "pinn_trainer_run: steps must be >= 0");
   if (!resample && !t->have_batch) return fail(h, PINN_EINVAL, "pinn_trainer_run: no batch yet (resample = 0 needs pinn_trainer_set_batch or an earlier sampled step)");
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   if (use_graph && !t->g_keep) {
     // one plain step first: one-time kernel attributes are set outside the capture
     if (steps == 0) return 0;
@@ -289,7 +295,7 @@ int pinn_trainer_read(pinn_trainer* t, double* theta, double* m, double* v, doub
                       int64_t history_rows) {
   if (!t) return PINN_EINVAL;
   pinn_handle* h = t->h;
-  CU(h, cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   CU(h, cudaStreamSynchronize(t->st));
   if (theta) CU(h, cudaMemcpy(theta, t->theta, NTHETA * 8, cudaMemcpyDeviceToHost));
   if (m) CU(h, cudaMemcpy(m, t->m, NTHETA * 8, cudaMemcpyDeviceToHost));

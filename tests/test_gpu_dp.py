@@ -185,3 +185,60 @@ def test_two_processes_over_ipc_match_nccl_allreduce(tmp_path, golden_dir):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(not two_gpus(), reason="needs two GPUs")
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_device_resident_training_loop_data_parallel(golden_dir, use_graph):
+    """Two device-resident trainers (one per GPU, exchange connected) with n/2 points each draw exactly the batch a single
+    trainer with n points draws (Philox counter = global point index), see the global set sizes (count exchange in the
+    sampler) and the global gradient (exchange in the reduction kernel): identical replicas on both ranks, and the same
+    trajectory as the one-GPU run up to the rounding of a different summation order (which it could not be if the
+    shards were not the two halves of the single-GPU batch: the loss of a fresh batch differs by O(10 %))."""
+    th0 = np.load(os.path.join(golden_dir, "trainpy_n2048.npz"))["theta"]
+    n, steps, seed = 8192, 8, 777
+    one = pk.Trainer("trainpy", n, th0, seed=seed, lr=8e-3, history_capacity=steps, device=0)
+    one.run(steps, use_graph=use_graph)
+    ref = one.read()
+    one.close()
+    hs = [pk.Handle.get(0), pk.Handle.get(1)]
+    for r in range(2):
+        hs[r].dp_init(r, 2, want_ipc=False)
+    trs = []
+    try:
+        for r in range(2):
+            hs[r].dp_connect_local(hs)
+        # one host thread per rank, as separate processes would be (the first graph step synchronises its stream, which
+        # needs the peer to be running: ctypes releases the GIL during the calls)
+        import threading
+        trs, out, errs = [None, None], [None, None], []
+
+        def rank_main(r):
+            try:
+                trs[r] = pk.Trainer("trainpy", n // 2, th0, seed=seed, lr=8e-3, history_capacity=steps, device=r)
+                trs[r].run(steps, use_graph=use_graph)
+                out[r] = trs[r].read()
+            except Exception as e:  # noqa: BLE001 - reported below
+                errs.append((r, e))
+
+        th = [threading.Thread(target=rank_main, args=(r,)) for r in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(120)
+        assert not errs, errs
+        assert hs[0].dp_status() == steps and hs[1].dp_status() == steps
+        for k in ("theta", "m", "v", "best_theta"):
+            assert np.array_equal(out[0][k], out[1][k]), k          # the replicas stay bit-identical
+        assert np.array_equal(out[0]["history"][:, :3], out[1]["history"][:, :3])
+        assert np.allclose(out[0]["history"][:, :3], ref["history"][:, :3], rtol=2e-5)
+        assert np.allclose(out[0]["history"][:, 3], ref["history"][:, 3], rtol=1e-5)   # mean E over the GLOBAL batch
+        assert np.abs(out[0]["theta"] - ref["theta"]).max() < 2e-4 * np.abs(ref["theta"]).max()
+    finally:
+        for t in trs:
+            if t is not None:
+                t.close()
+        for r in range(2):
+            torch.cuda.synchronize(r)
+        for r in range(2):
+            hs[r].dp_shutdown()
