@@ -315,8 +315,8 @@ def main():
 
     # ---- the whole training loop on the device (sampler -> loss/gradient -> Adam, CUDA-graph replay): N=1 only
     loop = None
-    if world == 1:
-        tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6)
+    if world == 1 or fused:
+        tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6, device=local)
         tr.run(20)
         tr.read()
         Kl = max(10, min(K, 300))
@@ -326,8 +326,12 @@ def main():
         tr.run(Kl)
         l1.record(ts)
         tr.read()
-        loop = {"value": n * Kl / (l0.elapsed_time(l1) * 1e-3), "unit": "points/s", "steps": Kl,
-                "what": "pinn_trainer: Philox sampler + fused loss/gradient + float64 Adam per step, one CUDA-graph replay each, no host sync"}
+        lms = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+        loop = {"value": n * world * Kl / (float(lms.item()) * 1e-3), "unit": "points/s", "steps": Kl,
+                "what": "pinn_trainer: Philox sampler + fused loss/gradient%s + float64 Adam per step, one CUDA-graph replay "
+                        "each, no host sync" % (" + set-size and gradient exchange over NVLink" if world > 1 else "")}
         tr.close()
 
     # ---- two more reference points for N = 1 (BASELINE configs 2 and 5) ----

@@ -32,7 +32,11 @@ __device__ long long g_timeline[16 * 32];
 extern "C" int pinn_debug_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)); }
 // whole-kernel stamps of warp 0 of CTA 0: [0] entry, [1] setup done, [2 + it] start of its it-th super-tile, [40] loop done, [41] end
 __device__ long long g_timeline_k[48];
-#define TLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_timeline_k[(i)] = clock64(); } while (0)
+__device__ long long g_timeline_cta[2 * 256];  // per CTA: globaltimer (ns) at entry and at exit
+extern "C" int pinn_debug_timeline_cta(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_timeline_cta, sizeof(g_timeline_cta)); }
+#define TLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_timeline_k[(i)] = clock64(); \
+                    if (threadIdx.x == 0 && ((i) == 0 || (i) == 41)) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+                      g_timeline_cta[blockIdx.x * 2 + ((i) == 41)] = (long long)t_; } } while (0)
 extern "C" int pinn_debug_timeline_kernel(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_timeline_k, sizeof(g_timeline_k)); }
 #else
 #define TL(i) do { } while (0)

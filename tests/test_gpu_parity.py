@@ -340,3 +340,71 @@ def test_argument_errors_do_not_crash(init_theta):
     with pytest.raises(pk.PinnError):
         h.check(h.L.pinn_fields(h.h, 0, 0, None, None, None, None, 0, None, None, None, None, None, None, None), "n=0")
     assert h.launch_count() >= 0
+
+
+# ---------------------------------------------------------------------------------------------
+# pointer alignment and host-memory paths of the coordinate stage (cp.async one super-tile ahead)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("off", [1, 2, 3])
+def test_unaligned_views_of_coordinates_mask_and_theta(init_theta, off):
+    """x,y,z,R only 4-byte aligned, the mask at an odd byte address (the kernel fetches the aligned word around each
+    mask byte), theta off the 16-byte boundary the TMA bulk copy wants (plain-load fallback): same bits as aligned."""
+    n = 3000 + off
+    a32, m1, m2 = sample(0, n, 71)
+    th32 = init_theta.astype(np.float32)
+    d = dev()
+    w = torch.tensor([1.0 / n, 1.0 / m1.sum(), 1.0 / m2.sum()], dtype=torch.float64, device=d)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    mk = (m1 + 2 * m2).astype(np.uint8)
+    s0, g0, _ = pk.loss_and_grad_raw(0, *[t(a) for a in a32], t(th32), t(mk), w)
+
+    def shifted(a, k):
+        buf = torch.zeros(a.size + 8, dtype=torch.from_numpy(a[:1]).dtype, device=d)
+        buf[k:k + a.size] = t(a)
+        v = buf[k:k + a.size]
+        assert v.data_ptr() % 16 != 0 or a.dtype == np.uint8
+        return v
+
+    s1, g1, _ = pk.loss_and_grad_raw(0, *[shifted(a, off) for a in a32], shifted(th32, off), shifted(mk, off), w)
+    assert torch.equal(s0[:7], s1[:7]) and torch.equal(g0, g1)
+    ref = oracle(0, th32, a32, m1, m2)
+    assert abs(s1.cpu().numpy()[0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_entry_pinned_in_place_equals_staged_pageable(init_theta, dtype):
+    """pinn_loss_fwd_bwd_host: page-locked inputs are read by the kernel in place over PCIe, pageable ones are staged
+    (one copy below 8 rounds of super-tiles, 4 overlapped chunks above): same results, explicit mask and derived sets,
+    float32 and float64 coordinates."""
+    import ctypes
+    h = pk.Handle.get(0)
+    for n in (5000, 200000):
+        a32, m1, m2 = sample(0, n, 81)
+        cols = [torch.from_numpy(a.astype(dtype)) for a in a32]
+        mk = torch.from_numpy((m1 + 2 * m2).astype(np.uint8))
+        th64 = init_theta.astype(np.float32).astype(np.float64)
+        wv = np.array([1.0 / n, 1.0 / m1.sum(), 1.0 / m2.sum()])
+        P = lambda a: ctypes.c_void_p(a.ctypes.data)
+        TP = lambda x: ctypes.c_void_p(x.data_ptr())
+        res = {}
+        for mode in ("pageable", "pinned"):
+            c = [x.pin_memory() for x in cols] if mode == "pinned" else cols
+            m = mk.pin_memory() if mode == "pinned" else mk
+            for use_mask in (True, False):
+                sums, dth = np.zeros(8), np.zeros(1521)
+                rc = h.L.pinn_loss_fwd_bwd_host(h.h, 0, n, TP(c[0]), TP(c[1]), TP(c[2]), TP(c[3]), 1 if dtype == np.float64 else 0,
+                                                TP(m) if use_mask else None, P(th64), P(wv), 0xFFFF, 17.5, P(sums), P(dth), None)
+                h.check(rc, "pinn_loss_fwd_bwd_host")
+                res[(mode, use_mask)] = (sums.copy(), dth.copy())
+        for use_mask in (True, False):
+            sa, ga = res[("pageable", use_mask)]
+            sb, gb = res[("pinned", use_mask)]
+            if n < 100000:   # one launch either way: identical bits; chunked staging only changes the summation order
+                assert np.array_equal(sa[:7], sb[:7]) and np.array_equal(ga, gb)
+            else:
+                assert np.allclose(sa[:7], sb[:7], rtol=2e-6) and rel(ga, gb) < 1e-5
+        assert abs(res[("pinned", True)][0][0] - res[("pinned", False)][0][0]) / res[("pinned", True)][0][0] < 1e-6
+        if n <= 5000:
+            ref = oracle(0, init_theta.astype(np.float32), a32, m1, m2)
+            assert abs(res[("pinned", True)][0][0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
+            check_tensors(res[("pinned", True)][1], ref["grad"], 1e-5)

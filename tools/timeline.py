@@ -27,7 +27,8 @@ x, y, z, R, i1, i2 = ra.sample_box(n, "poc", g)
 xs = [t.ravel().float().to(dev) for t in (x, y, z, R)]
 th = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "checkpoints.npz"))["ionHsym"].astype(np.float32)).to(dev)
 w = torch.tensor([1.0 / n, 2.0 / n, 2.0 / n], dtype=torch.float64, device=dev)
-for _ in range(3):
+warm = int(sys.argv[2]) if len(sys.argv) > 2 else 3   # many launches first = clocks ramped up like in a long run
+for _ in range(warm):
     pk.loss_and_grad_raw(variant, *xs, th, None, w)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (16 * 32))()
@@ -51,3 +52,20 @@ assert h.L.pinn_debug_timeline_kernel(kb) == 0
 k = np.array(kb[:])
 print("CTA 0, warp 0: setup %d cycles | first tiles %s | steady tile %d | epilogue (fold) %d cycles | kernel body %d cycles = %.1f us" % (
     k[1] - k[0], " ".join(str(int(k[3 + i] - k[2 + i])) for i in range(6)), k[10] - k[9], k[41] - k[40], k[41] - k[0], (k[41] - k[0]) / 1965.0))
+
+cb = (ctypes.c_longlong * 512)()
+assert h.L.pinn_debug_timeline_cta(cb) == 0
+c = np.array(cb[:]).reshape(256, 2)[:148]
+t0 = c[:, 0].min()
+print("CTA entry: first 0, median +%.2f us, last +%.2f us | CTA exit: first +%.2f us, median +%.2f us, last +%.2f us (globaltimer)" % (
+    (np.median(c[:, 0]) - t0) / 1e3, (c[:, 0].max() - t0) / 1e3, (c[:, 1].min() - t0) / 1e3, (np.median(c[:, 1]) - t0) / 1e3, (c[:, 1].max() - t0) / 1e3))
+# event-timed duration of the same launch, for the part outside the CTAs
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+hh = pk.Handle.get(0); hh.profile_begin()
+for _ in range(20):
+    pk.loss_and_grad_raw(variant, *xs, th, None, w)
+torch.cuda.synchronize()
+ms, cnt = hh.profile_collect()
+print("event-timed step kernel: %.2f us (instrumented build)" % (ms / cnt * 1e3))
+print("effective SM clock of that launch: %.0f MHz (CTA 0: %d cycles in %.2f us)" % (
+    (k[41] - k[0]) / ((c[0, 1] - c[0, 0]) / 1e3), k[41] - k[0], (c[0, 1] - c[0, 0]) / 1e3))
