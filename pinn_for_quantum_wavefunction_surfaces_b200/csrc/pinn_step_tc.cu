@@ -143,7 +143,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
   TL(1);
   tc_role_sync(c);
   TL(2);
-  if (c.issuer) {
+  if (c.issuer && elect_one()) {
     tc_fence_after();
     const uint32_t d = c.tbase + cb;
     const uint32_t bs = c.wts_saddr + (uint32_t)offsetof(Wts, BS), bsp = c.wts_saddr + (uint32_t)offsetof(Wts, BSP);
@@ -291,7 +291,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   TL(7);
   tc_role_sync(c);  // (also orders the stash writes above before the fragment loads below: bar.sync)
   TL(8);
-  if (c.issuer) {
+  if (c.issuer && elect_one()) {
     tc_fence_after();
     const uint32_t d = c.tbase + cb;
     const uint32_t bw = c.wts_saddr + (uint32_t)offsetof(Wts, BWT);
@@ -429,7 +429,7 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
   TL(1);
   tc_role_sync(c);
   TL(2);
-  if (c.issuer) {
+  if (c.issuer && elect_one()) {
     tc_fence_after();
     const uint32_t d = c.tbase + TC_E_BASE;
     const uint32_t be = c.wts_saddr + (uint32_t)offsetof(Wts, BE);
@@ -501,7 +501,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   TL(7);
   tc_role_sync(c);
   TL(8);
-  if (c.issuer) {
+  if (c.issuer && elect_one()) {
     tc_fence_after();
     const uint32_t d = c.tbase + TC_E_BASE;
     const uint32_t be = c.wts_saddr + (uint32_t)offsetof(Wts, BET);
@@ -603,7 +603,8 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
   unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - 2 * COORD_STAGE_BYTES;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role/group branches and MMA operands
   const int role = warp >> 2, grp = warp & 3;
   const bool is_mlp = role < NEV;
   const int sx = swz(lane);
@@ -658,12 +659,12 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   }
 
   TcCtx c;
-  c.tbase = *tmem_slot;
+  c.tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   c.tlane = c.tbase + ((uint32_t)(grp * 32) << 16);
   c.mbar = smem_u32(&mbars[1 + role]);
   c.phase = 0;
   c.bar_id = 5 + role;
-  c.issuer = (grp == 0) && (lane == 0);
+  c.issuer = (grp == 0);
   c.wts_saddr = smem_u32(&w);
   const uint32_t cb = is_mlp ? (uint32_t)role * TC_MLP_COLS : TC_E_BASE;
 

@@ -33,6 +33,12 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// one lane of a fully converged warp (the branch around it must be warp-uniform)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -126,7 +132,8 @@ struct TcCtx {
   uint32_t mbar;       // shared address of this role's mbarrier
   uint32_t phase;      // parity of the next completion
   int bar_id;          // named barrier of this role (128 threads)
-  bool issuer;         // the one thread of the role that issues its MMAs
+  bool issuer;         // this WARP issues the role's MMAs (warp-uniform; one elected lane does it, so that the operand
+                       // addresses stay in uniform registers and no per-thread broadcast loop is generated)
   uint32_t wts_saddr;  // shared address of the weight image
   int tl_it;           // tile counter (debug timeline builds)
 };
