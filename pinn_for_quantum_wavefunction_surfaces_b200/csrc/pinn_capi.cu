@@ -23,6 +23,16 @@ int pinn_version(void) { return 100; }
 int pinn_theta_size(void) { return NTHETA; }
 void pinn_theta_offsets(int* out) { memcpy(out, kOffsets, sizeof(kOffsets)); }
 
+// pinn_create: a failing CUDA call releases what was built so far; the message goes to the create-error slot
+#define CREATE_CU(call)                                    \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      pinn_destroy(h);                                     \
+      return fail(nullptr, (int)e__, "pinn_create: " #call); \
+    }                                                      \
+  } while (0)
+
 int pinn_create(int device, pinn_handle** out) {
   if (!out) return fail(nullptr, PINN_EINVAL, "pinn_create: out is NULL");
   *out = nullptr;
@@ -44,22 +54,22 @@ int pinn_create(int device, pinn_handle** out) {
     else if (!strcmp(e, "tcgen05")) h->engine = PINN_ENGINE_TCGEN05;
   }
   if (const char* e = getenv("PINN_B200_HOST_ZEROCOPY")) h->host_zero_copy = strcmp(e, "0") != 0;
-  CU(h, cudaMalloc(&h->wts, sizeof(Wts)));
+  CREATE_CU(cudaMalloc(&h->wts, sizeof(Wts)));
   // theta (1536 float) and the 3 loss weights share one block so that the *_host entry uploads both with one copy
-  CU(h, cudaMalloc(&h->theta_dev, HOST_IN_BYTES));
+  CREATE_CU(cudaMalloc(&h->theta_dev, HOST_IN_BYTES));
   h->weights_dev = reinterpret_cast<double*>(h->theta_dev + HOST_IN_THETA);
-  CU(h, cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
-  CU(h, cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
-  CU(h, cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
-  CU(h, cudaMalloc(&h->batch_counter, sizeof(unsigned long long)));
-  CU(h, cudaHostAlloc(&h->out_pinned, NPART * sizeof(double), cudaHostAllocMapped));
-  CU(h, cudaHostGetDevicePointer(&h->out_mapped, h->out_pinned, 0));
-  CU(h, cudaMallocHost(&h->theta_pinned, HOST_IN_BYTES));
+  CREATE_CU(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
+  CREATE_CU(cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
+  CREATE_CU(cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
+  CREATE_CU(cudaMalloc(&h->batch_counter, sizeof(unsigned long long)));
+  CREATE_CU(cudaHostAlloc(&h->out_pinned, NPART * sizeof(double), cudaHostAllocMapped));
+  CREATE_CU(cudaHostGetDevicePointer(&h->out_mapped, h->out_pinned, 0));
+  CREATE_CU(cudaMallocHost(&h->theta_pinned, HOST_IN_BYTES));
   h->weights_pinned = reinterpret_cast<double*>(h->theta_pinned + HOST_IN_THETA);
-  CU(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-  CU(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
-  CU(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-  for (int c = 0; c < 4; c++) CU(h, cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+  CREATE_CU(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  CREATE_CU(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+  CREATE_CU(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  for (int c = 0; c < 4; c++) CREATE_CU(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
   *out = h;
   return 0;
 }

@@ -156,6 +156,16 @@ int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, in
 // ---------------------------------------------------------------------------------------------
 // device-resident trainer
 // ---------------------------------------------------------------------------------------------
+// pinn_trainer_create: a failing CUDA call releases the partially built trainer
+#define TRAINER_CU(call)                                  \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) {                             \
+      pinn_trainer_destroy(t);                            \
+      return fail(h, (int)e__, "pinn_trainer_create: " #call); \
+    }                                                     \
+  } while (0)
+
 int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const double* theta0_host, pinn_trainer** out) {
   if (!h) return PINN_EINVAL;
   if (!cfg || !theta0_host || !out) return fail(h, PINN_EINVAL, "pinn_trainer_create: NULL pointer argument");
@@ -168,30 +178,30 @@ int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const doub
   t->h = h; t->cfg = *cfg;
   *out = nullptr;
   const size_t n = (size_t)cfg->n;
-  CU(h, cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
-  CU(h, cudaMalloc(&t->x, n * 4)); CU(h, cudaMalloc(&t->y, n * 4)); CU(h, cudaMalloc(&t->z, n * 4));
-  CU(h, cudaMalloc(&t->R, n * 4)); CU(h, cudaMalloc(&t->E, n * 4)); CU(h, cudaMalloc(&t->mask, n));
-  CU(h, cudaMalloc(&t->theta32, NPART * 4));
-  CU(h, cudaMalloc(&t->counts, 16)); CU(h, cudaMalloc(&t->batch, 8)); CU(h, cudaMalloc(&t->step, 8)); CU(h, cudaMalloc(&t->best_step, 8));
-  CU(h, cudaMalloc(&t->weights, 4 * 8));
-  CU(h, cudaMalloc(&t->theta, NPART * 8)); CU(h, cudaMalloc(&t->m, NPART * 8)); CU(h, cudaMalloc(&t->v, NPART * 8));
-  CU(h, cudaMalloc(&t->grad, NPART * 8)); CU(h, cudaMalloc(&t->sums, 8 * 8));
-  CU(h, cudaMalloc(&t->best_loss, 8)); CU(h, cudaMalloc(&t->best_theta, NPART * 8));
+  TRAINER_CU(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+  TRAINER_CU(cudaMalloc(&t->x, n * 4)); TRAINER_CU(cudaMalloc(&t->y, n * 4)); TRAINER_CU(cudaMalloc(&t->z, n * 4));
+  TRAINER_CU(cudaMalloc(&t->R, n * 4)); TRAINER_CU(cudaMalloc(&t->E, n * 4)); TRAINER_CU(cudaMalloc(&t->mask, n));
+  TRAINER_CU(cudaMalloc(&t->theta32, NPART * 4));
+  TRAINER_CU(cudaMalloc(&t->counts, 16)); TRAINER_CU(cudaMalloc(&t->batch, 8)); TRAINER_CU(cudaMalloc(&t->step, 8)); TRAINER_CU(cudaMalloc(&t->best_step, 8));
+  TRAINER_CU(cudaMalloc(&t->weights, 4 * 8));
+  TRAINER_CU(cudaMalloc(&t->theta, NPART * 8)); TRAINER_CU(cudaMalloc(&t->m, NPART * 8)); TRAINER_CU(cudaMalloc(&t->v, NPART * 8));
+  TRAINER_CU(cudaMalloc(&t->grad, NPART * 8)); TRAINER_CU(cudaMalloc(&t->sums, 8 * 8));
+  TRAINER_CU(cudaMalloc(&t->best_loss, 8)); TRAINER_CU(cudaMalloc(&t->best_theta, NPART * 8));
   if (cfg->history_capacity > 0) {
-    CU(h, cudaMalloc(&t->hist, (size_t)cfg->history_capacity * 4 * 8));
-    CU(h, cudaMemset(t->hist, 0, (size_t)cfg->history_capacity * 4 * 8));
+    TRAINER_CU(cudaMalloc(&t->hist, (size_t)cfg->history_capacity * 4 * 8));
+    TRAINER_CU(cudaMemset(t->hist, 0, (size_t)cfg->history_capacity * 4 * 8));
   }
-  CU(h, cudaMemset(t->m, 0, NPART * 8)); CU(h, cudaMemset(t->v, 0, NPART * 8));
-  CU(h, cudaMemset(t->batch, 0, 8)); CU(h, cudaMemset(t->step, 0, 8));
+  TRAINER_CU(cudaMemset(t->m, 0, NPART * 8)); TRAINER_CU(cudaMemset(t->v, 0, NPART * 8));
+  TRAINER_CU(cudaMemset(t->batch, 0, 8)); TRAINER_CU(cudaMemset(t->step, 0, 8));
   const long long neg1 = -1;
-  CU(h, cudaMemcpy(t->best_step, &neg1, 8, cudaMemcpyHostToDevice));
+  TRAINER_CU(cudaMemcpy(t->best_step, &neg1, 8, cudaMemcpyHostToDevice));
   const double llim = 10.0;  // poc/main.py:370 Llim = 10; train.py takes the first loss unconditionally
-  CU(h, cudaMemcpy(t->best_loss, &llim, 8, cudaMemcpyHostToDevice));
-  CU(h, cudaMemcpy(t->theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
-  CU(h, cudaMemcpy(t->best_theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
+  TRAINER_CU(cudaMemcpy(t->best_loss, &llim, 8, cudaMemcpyHostToDevice));
+  TRAINER_CU(cudaMemcpy(t->theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
+  TRAINER_CU(cudaMemcpy(t->best_theta, theta0_host, NTHETA * 8, cudaMemcpyHostToDevice));
   float th32[NTHETA];
   for (int i = 0; i < NTHETA; i++) th32[i] = (float)theta0_host[i];
-  CU(h, cudaMemcpy(t->theta32, th32, NTHETA * 4, cudaMemcpyHostToDevice));
+  TRAINER_CU(cudaMemcpy(t->theta32, th32, NTHETA * 4, cudaMemcpyHostToDevice));
   *out = t;
   return 0;
 }
