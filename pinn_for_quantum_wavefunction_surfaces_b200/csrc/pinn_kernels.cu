@@ -695,6 +695,10 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   __shared__ double tot[32];
   const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + e;
+  // launched as a programmatic dependent of the step kernel (which signals launch_dependents when its tile loop is
+  // done): this grid is set up while the step kernel folds its accumulators; the partial rows are complete and
+  // visible once the wait returns
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   double s = 0.0;
 #pragma unroll 5
   for (int r = sl; r < nrows; r += RED_SLICES) s += partials[(size_t)r * NPART + idx];
@@ -821,8 +825,17 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
                           double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st) {
-  reduce_partials_kernel<<<DP_BLOCKS, RED_SLICES * 32, 0, st>>>(partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(DP_BLOCKS);
+  cfg.blockDim = dim3(RED_SLICES * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
 }
 
 }  // namespace pinn

@@ -828,6 +828,8 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   }
 
   TLK(40);
+  // the reduction kernel behind this launch may be set up now (it waits for this grid to complete before it reads)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
   tc_fence_before();
   __syncthreads();
