@@ -75,6 +75,10 @@ int64_t pinn_launch_count(pinn_handle* h);
 int pinn_set_engine(pinn_handle* h, int engine);
 int pinn_get_engine(pinn_handle* h);
 
+/* Host-side wall-clock split of the last pinn_loss_fwd_bwd_host call on this handle, microseconds:
+ * {enqueue (argument checks, parameter conversion, launches), wait for the device, copy-out, total}. */
+int pinn_host_timing(pinn_handle* h, double* out4);
+
 /* Optional timing of the fused step kernel alone (bench.py's roofline figure): between begin and collect
  * every pinn_loss_fwd_bwd brackets its step-kernel launch with CUDA events on the caller's stream;
  * collect synchronises them and returns the summed duration and the number of launches. */

@@ -7,6 +7,7 @@ call sites:
 
 * ``PinnLossPoc`` / ``PinnLossTrainPy`` - ``torch.autograd.Function`` replacements of
   ``NN_ion.LossFunctions`` (poc/main.py:341-355) and of the inline block train.py:41-57
+* ``HostStep``        - the training evaluation on fixed host buffers, arguments bound once (``pinn_loss_fwd_bwd_host``)
 * ``fields``          - fused ``parametricPsi`` + ``hamiltonian`` (poc/main.py:321, 118)
 * ``patch_nn_ion``    - monkey-patches an ``NN_ion`` class so the reference training loop runs unchanged
 * ``run_train_py``    - runs the reference ``train.py`` with lines 41-57 routed through the kernel
@@ -21,7 +22,7 @@ from .params import (N_THETA, POC_TENSOR_NAMES, TRAINPY_TENSOR_NAMES, pack_poc, 
                      unpack_trainpy, FINE_TUNE_GRAD_MASK)
 from ._lib import lib, Handle, PinnError, library_path
 from .ops import (PinnLossPoc, PinnLossTrainPy, loss_poc, loss_trainpy, fields, loss_and_grad_raw,
-                  indices_to_mask)
+                  indices_to_mask, HostStep)
 from .patch import patch_nn_ion, run_train_py, trainpy_patched_source
 from . import analysis, convert, trainer
 from .trainer import Trainer, AdamState, adam_step, sample, train_trainpy, train_poc, init_trainpy
@@ -29,7 +30,7 @@ from .trainer import Trainer, AdamState, adam_step, sample, train_trainpy, train
 __all__ = [
     "N_THETA", "POC_TENSOR_NAMES", "TRAINPY_TENSOR_NAMES", "pack_poc", "unpack_poc", "pack_trainpy",
     "unpack_trainpy", "FINE_TUNE_GRAD_MASK", "lib", "Handle", "PinnError", "library_path", "PinnLossPoc",
-    "PinnLossTrainPy", "loss_poc", "loss_trainpy", "fields", "loss_and_grad_raw", "indices_to_mask",
+    "PinnLossTrainPy", "loss_poc", "loss_trainpy", "fields", "loss_and_grad_raw", "indices_to_mask", "HostStep",
     "patch_nn_ion", "run_train_py", "trainpy_patched_source", "analysis", "convert", "trainer", "Trainer", "AdamState",
     "adam_step", "sample", "train_trainpy", "train_poc", "init_trainpy",
 ]

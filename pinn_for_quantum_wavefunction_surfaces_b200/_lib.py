@@ -13,7 +13,7 @@ EXPORTS = [
     "pinn_sample", "pinn_adam_step", "pinn_enet_curve", "pinn_grid_reduce", "pinn_trainer_create", "pinn_trainer_destroy",
     "pinn_trainer_load_state", "pinn_trainer_set_batch", "pinn_trainer_run", "pinn_trainer_read", "pinn_trainer_batch",
     "pinn_trainer_stream",
-    "pinn_dp_init", "pinn_dp_connect", "pinn_dp_connect_local", "pinn_dp_enable", "pinn_dp_status", "pinn_dp_shutdown",
+    "pinn_host_timing", "pinn_dp_init", "pinn_dp_connect", "pinn_dp_connect_local", "pinn_dp_enable", "pinn_dp_status", "pinn_dp_shutdown",
 ]
 
 
@@ -106,6 +106,8 @@ def lib():
         L.pinn_trainer_batch.restype = i32
         L.pinn_trainer_stream.argtypes = [vp]
         L.pinn_trainer_stream.restype = vp
+        L.pinn_host_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+        L.pinn_host_timing.restype = i32
         L.pinn_dp_init.argtypes = [vp, i32, i32, vp]
         L.pinn_dp_init.restype = i32
         L.pinn_dp_connect.argtypes = [vp, vp]
@@ -200,6 +202,12 @@ class Handle:
 
     def dp_shutdown(self):
         self.check(self.L.pinn_dp_shutdown(self.h), "pinn_dp_shutdown")
+
+    def host_timing(self):
+        """-> dict(enqueue, wait, copy_out, total) in microseconds for the last pinn_loss_fwd_bwd_host call."""
+        a = (ctypes.c_double * 4)()
+        self.check(self.L.pinn_host_timing(self.h, a), "pinn_host_timing")
+        return {"enqueue": a[0], "wait": a[1], "copy_out": a[2], "total": a[3]}
 
     def close(self):
         if self.h:

@@ -1,4 +1,5 @@
 // C ABI of the PINN hot path (see include/pinn_b200.h for the contract).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,7 @@ int pinn_create(int device, pinn_handle** out) {
     else if (!strcmp(e, "tcgen05")) h->engine = PINN_ENGINE_TCGEN05;
   }
   if (const char* e = getenv("PINN_B200_HOST_ZEROCOPY")) h->host_zero_copy = strcmp(e, "0") != 0;
+  if (const char* e = getenv("PINN_B200_HOST_INLINE")) h->host_inline_params = strcmp(e, "0") != 0;
   CREATE_CU(cudaMalloc(&h->wts, sizeof(Wts)));
   // theta (1536 float) and the 3 loss weights share one block so that the *_host entry uploads both with one copy
   CREATE_CU(cudaMalloc(&h->theta_dev, HOST_IN_BYTES));
@@ -113,6 +115,12 @@ int pinn_set_engine(pinn_handle* h, int engine) {
   return 0;
 }
 int pinn_get_engine(pinn_handle* h) { return h ? h->engine : PINN_EINVAL; }
+
+int pinn_host_timing(pinn_handle* h, double* out4) {
+  if (!h || !out4) return PINN_EINVAL;
+  memcpy(out4, h->host_us, sizeof(h->host_us));
+  return 0;
+}
 
 int pinn_profile_begin(pinn_handle* h) {
   if (!h) return PINN_EINVAL;
@@ -307,37 +315,53 @@ static int enqueue_step_chunk(pinn_handle* h, int nev, StepParams p, int64_t fir
   return 0;
 }
 
-int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
-                      const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
-                      uint32_t grad_mask, float bcutoff, double* sums, double* dtheta, float* E_out, void* stream) {
-  if (!h) return PINN_EINVAL;
+// The training evaluation on device buffers.  theta / weights: device pointers, or (tcgen05 engine, used by the *_host
+// entry) NULL with theta_inline / weights_inline = HOST arrays that travel inside the kernel parameters.
+static int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                             const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
+                             const float* theta_inline, const double* weights_inline, uint32_t grad_mask, float bcutoff,
+                             double* sums, double* dtheta, float* E_out, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(h->mu);
   StepParams p{};
   int nev = 0;
   if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: unknown variant");
   if (n <= 0) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: n must be positive");
-  if (!x || !y || !z || !R || !theta || !sums || !dtheta)
+  if (!x || !y || !z || !R || (!theta && !theta_inline) || !sums || !dtheta)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
   DevGuard dev_guard(h->device);
-  cudaStream_t st = (cudaStream_t)stream;
   p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.bcut = bcutoff; p.partials = h->partials; p.E_out = E_out;
   p.base_grads = (grad_mask & 0x003Fu) != 0;
   p.gate_grads = (grad_mask & 0xF000u) != 0;
-  if (int rc = enqueue_prep(h, theta, p, st)) return rc;
-  if (!weights) {
-    CU(h, launch_count(p, h->counts, h->weights_dev, st));
-    h->launches += 2;
-    weights = h->weights_dev;
+  if (theta_inline) {
+    p.theta_inline = theta_inline;
+    p.weights_inline = weights_inline;
+  } else {
+    if (int rc = enqueue_prep(h, theta, p, st)) return rc;
+    if (!weights) {
+      CU(h, launch_count(p, h->counts, h->weights_dev, st));
+      h->launches += 2;
+      weights = h->weights_dev;
+    }
   }
   p.weights = weights;
   int grid = 0;
   int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
   if (rc) return rc;
-  CU(h, launch_reduce(h->partials, grid, weights, grad_mask, dtheta, sums, E_out, n, h->dp_on ? h->dp : DpArgs(), st));
+  CU(h, launch_reduce(h->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
+                      h->dp_on ? h->dp : DpArgs(), st));
   h->launches++;
   return 0;
+}
+
+int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                      const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
+                      uint32_t grad_mask, float bcutoff, double* sums, double* dtheta, float* E_out, void* stream) {
+  if (!h) return PINN_EINVAL;
+  if (!theta) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
+  return loss_fwd_bwd_impl(h, variant, n, x, y, z, R, in_dtype, mask, theta, weights, nullptr, nullptr, grad_mask, bcutoff, sums,
+                           dtheta, E_out, (cudaStream_t)stream);
 }
 
 int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z, const void* R,
@@ -371,6 +395,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: bad in_dtype");
+  const auto t_enter = std::chrono::steady_clock::now();
   DevGuard dev_guard(h->device);
   const size_t es = in_dtype == PINN_F64 ? 8 : 4;
   // Page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) inputs are read by the kernel in place: the
@@ -402,8 +427,15 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     memcpy(h->weights_pinned, weights_host, 3 * sizeof(double));
     wdev = h->weights_dev;
   }
-  CU(h, cudaMemcpyAsync(h->theta_dev, h->theta_pinned, weights_host ? HOST_IN_BYTES : NTHETA * sizeof(float),
-                        cudaMemcpyHostToDevice, st));
+  // tcgen05 engine with known weights: theta and the weights ride in the kernel parameters, nothing is uploaded first
+  const bool inline_params = weights_host && h->engine == PINN_ENGINE_TCGEN05 && h->host_inline_params;
+  if (!inline_params)
+    CU(h, cudaMemcpyAsync(h->theta_dev, h->theta_pinned, weights_host ? HOST_IN_BYTES : NTHETA * sizeof(float),
+                          cudaMemcpyHostToDevice, st));
+  const float* th_dev = inline_params ? nullptr : h->theta_dev;
+  const float* th_inl = inline_params ? h->theta_pinned : nullptr;
+  const double* w_inl = inline_params ? h->weights_pinned : nullptr;
+  if (inline_params) wdev = nullptr;
   // the 8 sums and 1521 gradients are written by the reduction kernel straight into mapped page-locked memory
   double* outp = h->out_mapped;
   uint8_t* mdev = mask ? (uint8_t*)(base + 4 * col) : nullptr;
@@ -438,12 +470,12 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     if (nchunk > 1) CU(h, cudaEventRecord(h->ev_chunk[c], sc));
   }
   if (zero_copy) {
-    int rc = pinn_loss_fwd_bwd(h, variant, n, mapped[0], mapped[1], mapped[2], mapped[3], in_dtype,
-                               (const uint8_t*)mapped[4], h->theta_dev, wdev, grad_mask, bcutoff, outp, outp + 8, edev, st);
+    int rc = loss_fwd_bwd_impl(h, variant, n, mapped[0], mapped[1], mapped[2], mapped[3], in_dtype, (const uint8_t*)mapped[4],
+                               th_dev, wdev, th_inl, w_inl, grad_mask, bcutoff, outp, outp + 8, edev, st);
     if (rc) return rc;
   } else if (nchunk == 1) {
-    int rc = pinn_loss_fwd_bwd(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev,
-                               h->theta_dev, wdev, grad_mask, bcutoff, outp, outp + 8, edev, st);
+    int rc = loss_fwd_bwd_impl(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev, th_dev, wdev,
+                               th_inl, w_inl, grad_mask, bcutoff, outp, outp + 8, edev, st);
     if (rc) return rc;
   } else {
     std::lock_guard<std::mutex> lk(h->mu);
@@ -454,7 +486,8 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     p.in_f64 = in_dtype == PINN_F64; p.bcut = bcutoff; p.E_out = edev; p.weights = wdev;
     p.base_grads = (grad_mask & 0x003Fu) != 0;
     p.gate_grads = (grad_mask & 0xF000u) != 0;
-    if (int rc = enqueue_prep(h, h->theta_dev, p, st)) return rc;
+    if (inline_params) { p.theta_inline = th_inl; p.weights_inline = w_inl; }
+    else if (int rc = enqueue_prep(h, h->theta_dev, p, st)) return rc;
     int rows = 0;
     for (int c = 0; c < nchunk; c++) {
       CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
@@ -463,13 +496,19 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
       if (rc) return rc;
       rows += r;
     }
-    CU(h, launch_reduce(h->partials, rows, wdev, grad_mask, outp + 8, outp, edev, n, h->dp_on ? h->dp : DpArgs(), st));
+    CU(h, launch_reduce(h->partials, rows, wdev, w_inl, grad_mask, outp + 8, outp, edev, n, h->dp_on ? h->dp : DpArgs(), st));
     h->launches++;
   }
   if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  const auto t_submitted = std::chrono::steady_clock::now();
   CU(h, cudaStreamSynchronize(st));
+  const auto t_done = std::chrono::steady_clock::now();
   memcpy(sums_host, h->out_pinned, 8 * sizeof(double));
   memcpy(dtheta_host, h->out_pinned + 8, NTHETA * sizeof(double));
+  const auto t_exit = std::chrono::steady_clock::now();
+  auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  h->host_us[0] = us(t_enter, t_submitted); h->host_us[1] = us(t_submitted, t_done); h->host_us[2] = us(t_done, t_exit);
+  h->host_us[3] = us(t_enter, t_exit);
   return 0;
 }
 

@@ -37,8 +37,10 @@ struct pinn_handle {
   DpArgs dp;
   bool dp_on = false;
   bool dp_opened[DP_MAX_WORLD] = {false, false, false, false, false, false, false, false};  // peer[r] came from cudaIpcOpenMemHandle
+  double host_us[4] = {0, 0, 0, 0};   // last pinn_loss_fwd_bwd_host call: submit, wait, copy-out, total (microseconds)
   int64_t launches = 0;
   int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
+  bool host_inline_params = true;     // *_host entry: theta + loss weights inside the kernel parameters (PINN_B200_HOST_INLINE=0: upload)
   bool host_zero_copy = true;         // pinn_loss_fwd_bwd_host reads page-locked inputs in place (PINN_B200_HOST_ZEROCOPY=0: stage)
   bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
   std::vector<cudaEvent_t> ev_pool;

@@ -687,8 +687,13 @@ __global__ void weights_from_counts_kernel(const unsigned long long* counts, lon
 // ---------------------------------------------------------------------------------------------
 constexpr int RED_SLICES = 32;
 static_assert(RED_SLICES >= DP_MAX_WORLD, "one row-slice of threads per data-parallel peer");
+struct RedWeights {  // loss weights by value (the *_host entry) instead of through device memory
+  double w[3];
+  int use;
+};
 __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
-                                                              const double* __restrict__ weights, uint32_t grad_mask,
+                                                              const double* __restrict__ weights, const RedWeights wi,
+                                                              uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
                                                               const float* __restrict__ E_out, long long n, const DpArgs dp) {
   __shared__ double sh[RED_SLICES][33];
@@ -772,7 +777,8 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   if (blockIdx.x == (S_RES2 / 32) && threadIdx.x == 0) {
     const int b = S_RES2 - (S_RES2 / 32) * 32;
     const double r2 = tot[b], p1 = tot[b + 1], p2 = tot[b + 2], sE = tot[b + 3];
-    const double Lpde = weights[0] * r2, Lbc = weights[1] * p1 + weights[2] * p2;
+    const double w0 = wi.use ? wi.w[0] : weights[0], w1 = wi.use ? wi.w[1] : weights[1], w2 = wi.use ? wi.w[2] : weights[2];
+    const double Lpde = w0 * r2, Lbc = w1 * p1 + w2 * p2;
     sums[0] = Lpde + Lbc; sums[1] = Lpde; sums[2] = Lbc; sums[3] = sE;
     sums[4] = r2; sums[5] = p1; sums[6] = p2;
     sums[7] = (E_out && n > 0) ? (double)E_out[n - 1] : 0.0;
@@ -823,8 +829,11 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
   return cudaGetLastError();
 }
 
-cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
-                          double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st) {
+cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
+                          uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
+                          cudaStream_t st) {
+  RedWeights wi{};
+  if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(DP_BLOCKS);
   cfg.blockDim = dim3(RED_SLICES * 32);
@@ -835,7 +844,7 @@ cudaError_t launch_reduce(const double* partials, int nrows, const double* weigh
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partials, nrows, weights, grad_mask, dtheta, sums, E_out, n, dp);
+  return cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp);
 }
 
 }  // namespace pinn

@@ -34,6 +34,10 @@ struct StepParams {
   VariantCoef vc;
   int base_grads, gate_grads;  // reverse sweeps wanted (fine-tune mode clears both)
   GridDesc grid;
+  // HOST pointers, read by the launchers only (tcgen05 engine, *_host entry): when set, theta (1521 float) and the three
+  // loss weights travel inside the kernel parameters instead of through a preceding host-to-device copy
+  const float* theta_inline;
+  const double* weights_inline;
 };
 
 cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
@@ -60,7 +64,9 @@ struct DpArgs {
   int rank = 0;
   unsigned char* peer[DP_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // exchange buffers, [rank] = own
 };
-cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, uint32_t grad_mask, double* dtheta,
-                          double* sums, const float* E_out, long long n, const DpArgs& dp, cudaStream_t st);
+// weights: device pointer, or NULL with weights_inline (host, 3 double) carried in the kernel parameters
+cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
+                          uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
+                          cudaStream_t st);
 
 }  // namespace pinn

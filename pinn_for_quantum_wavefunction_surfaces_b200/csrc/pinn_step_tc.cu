@@ -22,6 +22,9 @@
 //     ~40 cycles per point and overlaps the element-wise work of the other roles; the weight-gradient
 //     contractions (K = points) stay on mma.sync, reading the shared-memory stash, and are issued while
 //     the reverse-sweep MMAs are in flight.
+#include <cstring>
+#include <type_traits>
+
 #include "pinn_tc.cuh"
 
 // Debug builds only (-DPINN_TIMELINE, tools/timeline.py): warp-level clock64() stamps at the phase boundaries of one
@@ -51,7 +54,7 @@ __host__ __device__ constexpr int tc_group_stash_floats() { return NEV * EVAL_ST
 template <int NEV>
 __host__ __device__ constexpr size_t tc_smem_bytes() {
   return WTS_TC_BYTES + 64 /*mbarriers + tmem base*/ + sizeof(float2) * 4 * 2 * 3 * 32 + sizeof(float) * 4 * tc_group_stash_floats<NEV>() +
-         2 * COORD_STAGE_BYTES;
+         COORD_STAGES * COORD_STAGE_BYTES;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -68,6 +71,11 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all but the newest COORD_AHEAD - 1 groups have landed
+__device__ __forceinline__ void cp_async_wait_next() {
+  if (COORD_AHEAD == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else asm volatile("cp.async.wait_group 1;" ::: "memory");
+}
 
 // issued by the E-net warp of a group for the group's 32 points (slot = 32 * group + lane of the super-tile)
 __device__ __forceinline__ void coord_stage_issue(const StepParams& p, unsigned char* buf, int slot, long long i) {
@@ -592,8 +600,22 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
 // the fused kernel.  NEV = MLP evaluations per point (2: poc, 1: train.py); TRAIN = with reverse sweep
 //   warp = role * 4 + group;  role < NEV: MLP evaluation, role == NEV: E-net + gate
 // ---------------------------------------------------------------------------------------------
-template <int NEV, bool TRAIN>
-__global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const StepParams p) {
+// Kernel parameters: the launch description; the INLINE instantiations (the *_host entry) also carry theta and the loss
+// weights by value (6 KB of parameter space; sm_100 takes up to 32 KB), so that no host-to-device copy has to precede
+// the kernel.
+struct TcParamsPlain {
+  StepParams p;
+};
+struct TcParamsInline {
+  StepParams p;
+  double w[4];
+  alignas(16) float theta[NTHETA + 3];
+};
+
+template <int NEV, bool TRAIN, bool INLINE>
+__global__ void __launch_bounds__((NEV + 1) * 128, 1)
+pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, TcParamsInline, TcParamsPlain>::type q) {
+  const StepParams& p = q.p;
   constexpr int G = 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Wts& w = *reinterpret_cast<Wts*>(smem_raw);  // only the first WTS_TC_BYTES are staged / valid
@@ -601,7 +623,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + WTS_TC_BYTES + 32);
   float2* mbox = reinterpret_cast<float2*>(smem_raw + WTS_TC_BYTES + 64);
   float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
-  unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - 2 * COORD_STAGE_BYTES;
+  unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - COORD_STAGES * COORD_STAGE_BYTES;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role/group branches and MMA operands
@@ -629,6 +651,11 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     const long long i0 = (long long)blockIdx.x * 128 + slot;
     coord_stage_issue(p, cstage, slot, i0 < p.n ? i0 : p.n - 1);
     cp_async_commit();
+    if (COORD_AHEAD == 2) {  // and the second one
+      const long long i1 = i0 + (long long)gridDim.x * 128;
+      if ((long long)blockIdx.x + gridDim.x < ((p.n + 127) >> 7)) coord_stage_issue(p, cstage + COORD_STAGE_BYTES, slot, i1 < p.n ? i1 : p.n - 1);
+      cp_async_commit();
+    }
   }
 
   // ---- weights: theta arrives in shared memory by ONE TMA bulk copy (6080 of its 6084 bytes; bulk copies move multiples
@@ -638,7 +665,16 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     float* th_s = stash;  // the stash is free until the first super-tile
     constexpr uint32_t TH_BULK = (NTHETA * 4 / 16) * 16;
     const bool bulk_ok = ((uintptr_t)p.theta & 15u) == 0;
-    if (bulk_ok) {
+    if constexpr (INLINE) {
+      // theta came with the kernel parameters: warp-uniform 16-byte reads (the constant cache serves one address per
+      // request), lanes 0..3 scatter the four values
+      const float4* src = reinterpret_cast<const float4*>(q.theta);
+      for (int j = warp; j < (NTHETA + 3) / 4; j += (NEV + 1) * 4) {
+        const float4 v = src[j];
+        const float val = lane == 0 ? v.x : lane == 1 ? v.y : lane == 2 ? v.z : v.w;
+        if (lane < 4 && 4 * j + lane < NTHETA) th_s[4 * j + lane] = val;
+      }
+    } else if (bulk_ok) {
       if (tid == 32) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbars[0])), "r"(TH_BULK) : "memory");
         asm volatile(
@@ -674,7 +710,10 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   float2* gbox = mbox + grp * (2 * 3 * 32);
 
   double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
-  if (TRAIN) { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
+  if (TRAIN) {
+    if constexpr (INLINE) { wpde = q.w[0]; wbc1 = q.w[1]; wbc2 = q.w[2]; }
+    else { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
+  }
   const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
   const float sN = p.vc.sN, cL = p.vc.cL, cV = p.vc.cV, cE = p.vc.cE;
 
@@ -693,7 +732,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
   // 32 points lie beyond n compute on a clamped index with zero weight
   const long long nsuper = (p.n + 127) >> 7;
   int it = 0;
-  if (stager) cp_async_wait_all();  // the first super-tile's coordinates (requested before the weight image was built)
+  if (stager) cp_async_wait_next();  // the first super-tile's coordinates (requested before the weight image was built)
   __syncthreads();
   TLK(1);
   for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
@@ -703,13 +742,14 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
     c.tl_it = it;
     TL(0);
     if (it < 38) TLK(2 + it);
-    const unsigned char* cbuf = cstage + (it & 1) * COORD_STAGE_BYTES;
+    const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
     const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
     const Geom g = geom_from_raw(raw);
     const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
-    if (stager) {  // coordinates of the next super-tile: in flight during this one, complete before the group barrier
-      const long long in = pidx + (long long)gridDim.x * 128;
-      if (st + gridDim.x < nsuper) coord_stage_issue(p, cstage + ((it + 1) & 1) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
+    if (stager) {  // coordinates COORD_AHEAD super-tiles ahead: in flight while this one (and the next) is computed
+      const long long in = pidx + (long long)COORD_AHEAD * gridDim.x * 128;
+      if (st + (long long)COORD_AHEAD * gridDim.x < nsuper)
+        coord_stage_issue(p, cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
       cp_async_commit();
     }
     float2* box = gbox + (it & 1) * (3 * 32);
@@ -731,7 +771,7 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
       box[2 * 32 + lane] = make_float2(E, gt);
     }
     TL(5);
-    if (stager) cp_async_wait_all();  // next tile's coordinates have landed; the barrier publishes them to the group
+    if (stager) cp_async_wait_next();  // the NEXT tile's coordinates have landed; the barrier publishes them to the group
     named_barrier(1 + grp, (NEV + 1) * 32);
     TL(6);
 
@@ -914,9 +954,9 @@ __global__ void __launch_bounds__((NEV + 1) * 128, 1) pinn_step_tc_kernel(const 
 // =================================================================================================
 // host-side launcher
 // =================================================================================================
-template <int NEV, bool TRAIN>
+template <int NEV, bool TRAIN, bool INLINE>
 static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t st) {
-  auto kern = pinn_step_tc_kernel<NEV, TRAIN>;
+  auto kern = pinn_step_tc_kernel<NEV, TRAIN, INLINE>;
   constexpr size_t smem = tc_smem_bytes<NEV>();
   static bool configured[16] = {false};
   int dev = 0;
@@ -926,7 +966,19 @@ static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t 
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  kern<<<grid, (NEV + 1) * 128, smem, st>>>(p);
+  if constexpr (INLINE) {
+    TcParamsInline q;
+    q.p = p;
+    memcpy(q.theta, p.theta_inline, NTHETA * sizeof(float));
+    q.theta[NTHETA] = q.theta[NTHETA + 1] = q.theta[NTHETA + 2] = 0.0f;
+    q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0.0;
+    if (p.weights_inline) memcpy(q.w, p.weights_inline, 3 * sizeof(double));
+    kern<<<grid, (NEV + 1) * 128, smem, st>>>(q);
+  } else {
+    TcParamsPlain q;
+    q.p = p;
+    kern<<<grid, (NEV + 1) * 128, smem, st>>>(q);
+  }
   return cudaGetLastError();
 }
 
@@ -949,8 +1001,10 @@ cudaError_t launch_grid_finish(const double* partials, int nrows, double* out, c
 }
 
 cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
-  if (nev == 2) return train ? launch_step_tc_t<2, true>(p, grid, st) : launch_step_tc_t<2, false>(p, grid, st);
-  return train ? launch_step_tc_t<1, true>(p, grid, st) : launch_step_tc_t<1, false>(p, grid, st);
+  if (train && p.theta_inline)
+    return nev == 2 ? launch_step_tc_t<2, true, true>(p, grid, st) : launch_step_tc_t<1, true, true>(p, grid, st);
+  if (nev == 2) return train ? launch_step_tc_t<2, true, false>(p, grid, st) : launch_step_tc_t<2, false, false>(p, grid, st);
+  return train ? launch_step_tc_t<1, true, false>(p, grid, st) : launch_step_tc_t<1, false, false>(p, grid, st);
 }
 
 }  // namespace pinn

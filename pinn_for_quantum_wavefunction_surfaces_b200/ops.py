@@ -101,6 +101,52 @@ def _host_step(variant, x, y, z, R, theta64, mask, weights, grad_mask, want_E, b
     return sums, dtheta, E_out
 
 
+class HostStep:
+    """A training evaluation on one fixed set of HOST buffers, prepared once and called many times
+    (``pinn_loss_fwd_bwd_host``).  Binding the 16 ctypes arguments costs ~15 microseconds in Python, an order of
+    magnitude more than the library needs to enqueue the work; a loop that reuses its batch buffers (the reference's
+    training loops do) prepares the call once per buffer set.  Pin the tensors (``tensor.pin_memory()``) to let the
+    kernel read them in place.
+
+        step = HostStep("poc", x, y, z, R)            # CPU float32/float64 tensors, (n,) or (n,1); optional uint8 mask
+        sums, dtheta = step(theta64, weights)         # numpy float64 (1521,), (3,) -> views of reused float64 outputs
+    """
+
+    def __init__(self, variant, x, y, z, R, mask=None, grad_mask=0xFFFF, bcutoff=BC_CUTOFF, device=None):
+        if not torch.cuda.is_available():
+            raise PinnError("no CUDA device: the PINN hot path has no CPU fallback")
+        import numpy as np
+        self.h = Handle.get(torch.cuda.current_device() if device is None else device)
+        self._keep = [_col(t, nm) for t, nm in ((x, "x"), (y, "y"), (z, "z"), (R, "R"))]
+        if any(t.is_cuda for t in self._keep):
+            raise ValueError("HostStep is for host tensors; use loss_and_grad_raw for CUDA tensors")
+        n = self._keep[0].numel()
+        for t in self._keep[1:]:
+            if t.dtype != self._keep[0].dtype or t.numel() != n:
+                raise ValueError("x,y,z,R must share dtype and length")
+        self._mask = None if mask is None else mask.detach().reshape(-1).to(torch.uint8).contiguous()
+        self.sums = np.zeros(8)
+        self.dtheta = np.zeros(P.N_THETA)
+        vp = ctypes.c_void_p
+        self._fn = self.h.L.pinn_loss_fwd_bwd_host
+        self._head = (self.h.h, int({"poc": 0, "trainpy": 1}.get(variant, variant)), n) + tuple(vp(t.data_ptr()) for t in self._keep) + (
+            _F64 if self._keep[0].dtype == torch.float64 else _F32, None if self._mask is None else vp(self._mask.data_ptr()))
+        self._th = self._w = self._thp = self._wp = None
+        self._tail = (int(grad_mask), float(bcutoff), vp(self.sums.ctypes.data), vp(self.dtheta.ctypes.data), None)
+
+    def __call__(self, theta64, weights=None):
+        """theta64: contiguous numpy float64 (1521,); weights: contiguous numpy float64 (3,) {1/n, 1/|set1|, 1/|set2|} or
+        None (sets counted on the device).  Returns (sums[8], dtheta[1521]); the arrays are overwritten by the next call."""
+        if theta64 is not self._th:       # `.ctypes.data` is slow; the usual caller passes the same arrays every step
+            self._th, self._thp = theta64, theta64.ctypes.data
+        if weights is not self._w:
+            self._w, self._wp = weights, (None if weights is None else weights.ctypes.data)
+        rc = self._fn(*self._head, self._thp, self._wp, *self._tail)
+        if rc:
+            self.h.check(rc, "pinn_loss_fwd_bwd_host")
+        return self.sums, self.dtheta
+
+
 class _PinnLoss(torch.autograd.Function):
     """forward(variant, order, x, y, z, R, idx1, idx2, *16 params) -> (Ltot, Lpde, Lbc, E)."""
 

@@ -408,3 +408,22 @@ def test_host_entry_pinned_in_place_equals_staged_pageable(init_theta, dtype):
             ref = oracle(0, init_theta.astype(np.float32), a32, m1, m2)
             assert abs(res[("pinned", True)][0][0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
             check_tensors(res[("pinned", True)][1], ref["grad"], 1e-5)
+
+
+def test_prepared_host_step_equals_the_plain_host_call(init_theta):
+    """ops.HostStep (arguments bound once) against the float64 oracle and against loss_trainpy on the same CPU tensors."""
+    a32, m1, m2 = sample(1, 3000, 91)
+    cols = [torch.from_numpy(a.astype(np.float64)).pin_memory() for a in a32]
+    mk = torch.from_numpy((m1 + 2 * m2).astype(np.uint8)).pin_memory()
+    step = pk.HostStep("trainpy", *cols, mask=mk)
+    th64 = np.ascontiguousarray(init_theta.astype(np.float32).astype(np.float64))
+    w = np.array([1.0 / 3000, 1.0 / m1.sum(), 1.0 / m2.sum()])
+    ref = oracle(1, init_theta.astype(np.float32), a32, m1, m2)
+    for _ in range(3):   # the output arrays are reused
+        sums, dth = step(th64, w)
+        assert abs(sums[0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
+        check_tensors(dth, ref["grad"], 1e-5)
+    s2, d2 = pk.HostStep("trainpy", *cols)(th64)     # sets and weights derived on the device
+    assert abs(s2[0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
+    t = pk.Handle.get(0).host_timing()
+    assert t["total"] > 0 and abs(t["enqueue"] + t["wait"] + t["copy_out"] - t["total"]) < 1.0
