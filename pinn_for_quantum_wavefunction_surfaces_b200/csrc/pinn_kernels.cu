@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   // launched as a programmatic dependent of the step kernel (which signals launch_dependents when its tile loop is
   // done): this grid is set up while the step kernel folds its accumulators; the partial rows are complete and
   // visible once the wait returns
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_wait();
   double s = 0.0;
 #pragma unroll 5
   for (int r = sl; r < nrows; r += RED_SLICES) s += partials[(size_t)r * NPART + idx];
@@ -834,17 +834,8 @@ cudaError_t launch_reduce(const double* partials, int nrows, const double* weigh
                           cudaStream_t st) {
   RedWeights wi{};
   if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(DP_BLOCKS);
-  cfg.blockDim = dim3(RED_SLICES * 32);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp);
+  return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS), dim3(RED_SLICES * 32), 0, st, partials, nrows, weights, wi, grad_mask, dtheta,
+                    sums, E_out, n, dp);
 }
 
 }  // namespace pinn

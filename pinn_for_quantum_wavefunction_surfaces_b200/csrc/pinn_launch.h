@@ -40,6 +40,29 @@ struct StepParams {
   const double* weights_inline;
 };
 
+// Launch as a programmatic dependent of the kernel in front of it in the stream: the grid may be set up (and, where
+// resources allow, its CTAs made resident) while that kernel drains.  Every kernel launched this way executes
+// griddepcontrol.wait (pdl_wait) before its first global-memory access, which returns once the kernel in front has
+// completed and its writes are visible - stream semantics are unchanged, only launch latency is hidden.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
 int step_groups();
 // tcgen05 engine (pinn_step_tc.cu): super-tiles of 128 points, one persistent CTA per SM

@@ -645,6 +645,9 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // launched as a programmatic dependent (launch_pdl): everything above needs no global memory and overlaps the tail of
+  // the kernel in front (reduction / Adam / sampler); from here on their results are read
+  pdl_wait();
   const int slot = grp * 32 + lane;
   const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
   if (stager) {
@@ -869,7 +872,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
 
   TLK(40);
   // the reduction kernel behind this launch may be set up now (it waits for this grid to complete before it reads)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_launch_dependents();
   // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
   tc_fence_before();
   __syncthreads();
@@ -973,13 +976,12 @@ static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t 
     q.theta[NTHETA] = q.theta[NTHETA + 1] = q.theta[NTHETA + 2] = 0.0f;
     q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0.0;
     if (p.weights_inline) memcpy(q.w, p.weights_inline, 3 * sizeof(double));
-    kern<<<grid, (NEV + 1) * 128, smem, st>>>(q);
+    return launch_pdl(kern, dim3(grid), dim3((NEV + 1) * 128), smem, st, q);
   } else {
     TcParamsPlain q;
     q.p = p;
-    kern<<<grid, (NEV + 1) * 128, smem, st>>>(q);
+    return launch_pdl(kern, dim3(grid), dim3((NEV + 1) * 128), smem, st, q);
   }
-  return cudaGetLastError();
 }
 
 // adds the per-CTA quadrature rows in a fixed order; out[5] = E(R) stored behind the rows

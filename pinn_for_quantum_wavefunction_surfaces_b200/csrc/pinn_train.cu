@@ -32,6 +32,7 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 // x, y, z, R.  Clamp and sets follow the reference literally: both tests use the radii of the UN-clamped point
 // (train.py:32-35), the clamp writes the VALUE `cutoff` into x, and the sets are taken after it (train.py:36-39).
 __global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
+  pdl_wait();
   const unsigned long long batch = *s.batch_counter;
   unsigned c1 = 0, c2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
@@ -75,6 +76,7 @@ __global__ void sample_finish_kernel(const unsigned long long* counts, long long
                                      const DpArgs dp) {
   __shared__ unsigned long long c[DP_MAX_WORLD][2];
   const int lane = threadIdx.x;
+  pdl_wait();
   unsigned long long c1 = counts[0], c2 = counts[1];
   long long ntot = n;
   if (dp.world > 1) {
@@ -124,9 +126,9 @@ cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& 
   if (e != cudaSuccess) return e;
   long long blocks = (s.n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sample_kernel<<<(int)blocks, 256, 0, st>>>(s);
-  sample_finish_kernel<<<1, 32, 0, st>>>(s.counts, s.n, weights, s.batch_counter, dp);
-  return cudaGetLastError();
+  e = launch_pdl(sample_kernel, dim3((unsigned)blocks), dim3(256), 0, st, s);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(sample_finish_kernel, dim3(1), dim3(32), 0, st, (const unsigned long long*)s.counts, s.n, weights, s.batch_counter, dp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -135,6 +137,7 @@ cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) adam_kernel(const AdamParams a) {
   __shared__ int take_best;
+  pdl_wait();
   const unsigned long long t = *a.step;  // optimizer steps done so far = index tt of this step in the reference loops
   const double Ltot = a.sums[0];
   if (threadIdx.x == 0) {
@@ -180,8 +183,7 @@ __global__ void __launch_bounds__(1024) adam_kernel(const AdamParams a) {
 }
 
 cudaError_t launch_adam(const AdamParams& a, cudaStream_t st) {
-  adam_kernel<<<1, 1024, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(adam_kernel, dim3(1), dim3(1024), 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------
