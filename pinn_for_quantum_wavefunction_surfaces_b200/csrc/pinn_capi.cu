@@ -63,7 +63,8 @@ int pinn_create(int device, pinn_handle** out) {
   CREATE_CU(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
   CREATE_CU(cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
   CREATE_CU(cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
-  CREATE_CU(cudaMalloc(&h->batch_counter, sizeof(unsigned long long)));
+  CREATE_CU(cudaMalloc(&h->batch_counter, 2 * sizeof(unsigned long long)));  // [0] batch index of pinn_sample, [1] its block ticket
+  CREATE_CU(cudaMemset(h->batch_counter, 0, 2 * sizeof(unsigned long long)));
   CREATE_CU(cudaHostAlloc(&h->out_pinned, NPART * sizeof(double), cudaHostAllocMapped));
   CREATE_CU(cudaHostGetDevicePointer(&h->out_mapped, h->out_pinned, 0));
   CREATE_CU(cudaMallocHost(&h->theta_pinned, HOST_IN_BYTES));
@@ -317,10 +318,13 @@ static int enqueue_step_chunk(pinn_handle* h, int nev, StepParams p, int64_t fir
 
 // The training evaluation on device buffers.  theta / weights: device pointers, or (tcgen05 engine, used by the *_host
 // entry) NULL with theta_inline / weights_inline = HOST arrays that travel inside the kernel parameters.
-static int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
-                             const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
-                             const float* theta_inline, const double* weights_inline, uint32_t grad_mask, float bcutoff,
-                             double* sums, double* dtheta, float* E_out, cudaStream_t st) {
+}  // extern "C"
+
+int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                      const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
+                      const float* theta_inline, const double* weights_inline, uint32_t grad_mask, float bcutoff,
+                      double* sums, double* dtheta, float* E_out, cudaStream_t st, const AdamParams* adam,
+                      unsigned long long* adam_ticket) {
   std::lock_guard<std::mutex> lk(h->mu);
   StepParams p{};
   int nev = 0;
@@ -350,10 +354,12 @@ static int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void*
   int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
   if (rc) return rc;
   CU(h, launch_reduce(h->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
-                      h->dp_on ? h->dp : DpArgs(), st));
+                      h->dp_on ? h->dp : DpArgs(), st, adam, adam_ticket));
   h->launches++;
   return 0;
 }
+
+extern "C" {
 
 int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
                       const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,

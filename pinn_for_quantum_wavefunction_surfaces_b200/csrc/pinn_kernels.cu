@@ -22,6 +22,7 @@
 //   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
 //     in double precision in a fixed order (deterministic).
 #include "pinn_device.cuh"
+#include "pinn_train.h"
 
 namespace pinn {
 
@@ -691,13 +692,23 @@ struct RedWeights {  // loss weights by value (the *_host entry) instead of thro
   double w[3];
   int use;
 };
+// Optimizer step fused behind the reduction (the device-resident trainer): every block updates the 32 parameters whose
+// gradient it has just completed; the block that finishes last does the once-per-step bookkeeping.
+struct AdamFuse {
+  int on;
+  AdamParams a;
+  unsigned long long* ticket;  // device, zero between launches
+};
 __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
                                                               const double* __restrict__ weights, const RedWeights wi,
                                                               uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
-                                                              const float* __restrict__ E_out, long long n, const DpArgs dp) {
+                                                              const float* __restrict__ E_out, long long n, const DpArgs dp,
+                                                              const AdamFuse ad) {
   __shared__ double sh[RED_SLICES][33];
   __shared__ double tot[32];
+  __shared__ double l3[3];
+  __shared__ int flag_s;
   const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + e;
   // launched as a programmatic dependent of the step kernel (which signals launch_dependents when its tile loop is
@@ -709,12 +720,14 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   for (int r = sl; r < nrows; r += RED_SLICES) s += partials[(size_t)r * NPART + idx];
   sh[sl][e] = s;
   __syncthreads();
+  unsigned int step = 0;
+  size_t slot = 0;
   if (dp.world > 1) {
     unsigned char* own = dp.peer[dp.rank];
     unsigned long long* ctl = reinterpret_cast<unsigned long long*>(own + DP_ROWS_BYTES);
     const unsigned long long step64 = ld_acquire_sys(&ctl[0]) + 1;  // ctl[0] = exchanges completed on this rank
-    const unsigned int step = (unsigned int)step64;
-    const size_t slot = (size_t)(step64 & 1ull) * DP_MAX_WORLD;
+    step = (unsigned int)step64;
+    slot = (size_t)(step64 & 1ull) * DP_MAX_WORLD;
     if (sl == 0) {
       double t = 0.0;
 #pragma unroll
@@ -774,14 +787,77 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
     }
   }
   __syncthreads();
-  if (blockIdx.x == (S_RES2 / 32) && threadIdx.x == 0) {
-    const int b = S_RES2 - (S_RES2 / 32) * 32;
+  const double w0 = wi.use ? wi.w[0] : weights[0], w1 = wi.use ? wi.w[1] : weights[1], w2 = wi.use ? wi.w[2] : weights[2];
+  constexpr int SB = S_RES2 / 32, b = S_RES2 - SB * 32;   // the block / lane that own the loss sums
+  if (blockIdx.x == SB && threadIdx.x == 0) {
     const double r2 = tot[b], p1 = tot[b + 1], p2 = tot[b + 2], sE = tot[b + 3];
-    const double w0 = wi.use ? wi.w[0] : weights[0], w1 = wi.use ? wi.w[1] : weights[1], w2 = wi.use ? wi.w[2] : weights[2];
     const double Lpde = w0 * r2, Lbc = w1 * p1 + w2 * p2;
     sums[0] = Lpde + Lbc; sums[1] = Lpde; sums[2] = Lbc; sums[3] = sE;
     sums[4] = r2; sums[5] = p1; sums[6] = p2;
     sums[7] = (E_out && n > 0) ? (double)E_out[n - 1] : 0.0;
+  }
+  if (!ad.on) return;
+
+  // ---- fused optimizer step.  Every block needs Ltot for the best-model rule: the blocks that do not own the loss
+  //      sums add those three entries themselves, in exactly the order used above (row slices, then slices in order,
+  //      then ranks in order), so that all blocks - and all ranks - decide on identical bits ----
+  if (blockIdx.x == SB) {
+    if (threadIdx.x < 3) l3[threadIdx.x] = tot[b + threadIdx.x];
+  } else {
+    if (threadIdx.x < 96) {
+      const int j = threadIdx.x >> 5, sj = threadIdx.x & 31;
+      double ps = 0.0;
+#pragma unroll 5
+      for (int r = sj; r < nrows; r += RED_SLICES) ps += partials[(size_t)r * NPART + S_RES2 + j];
+      sh[sj][j] = ps;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      const int j = threadIdx.x;
+      double local = 0.0;
+#pragma unroll
+      for (int i = 0; i < RED_SLICES; i++) local += sh[i][j];
+      double g = local;
+      if (dp.world > 1) {
+        const unsigned char* own = dp.peer[dp.rank];
+        g = 0.0;
+        for (int r = 0; r < dp.world; r++) {
+          double v = local;
+          if (r != dp.rank) {  // the peer's block SB deposits this entry in our buffer; only read here
+            const unsigned int* src = reinterpret_cast<const unsigned int*>(own) + ((slot + r) * NPART + S_RES2 + j) * 4;
+            const long long t0 = clock64();
+            uint2 lo, hi;
+            for (;;) {
+              lo = ld_relaxed_sys_v2(src);
+              hi = ld_relaxed_sys_v2(src + 2);
+              if ((lo.y == step && hi.y == step) || clock64() - t0 > 6000000000ll) break;
+            }
+            v = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+          }
+          g += v;
+        }
+      }
+      l3[j] = g;
+    }
+  }
+  __syncthreads();
+  const AdamParams& a = ad.a;
+  const unsigned long long tstep = *a.step;  // read before any block can finish the step (the last block advances it)
+  const double Lpde = w0 * l3[0], Lbc = w1 * l3[1] + w2 * l3[2];
+  const double Ltot = Lpde + Lbc;
+  const bool take_best = adam_take_best(a, tstep, Ltot);
+  if (sl == 0 && idx < NTHETA) adam_update_entry(a, adam_coef(a, tstep), idx, tot[e], take_best);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    flag_s = atomicAdd(ad.ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+    if (flag_s) {  // every block has updated its parameters and read the step / best loss; the loss sums are visible
+      __threadfence();
+      const double sv[8] = {ld_acquire_gpu(&sums[0]), ld_acquire_gpu(&sums[1]), ld_acquire_gpu(&sums[2]), ld_acquire_gpu(&sums[3]),
+                            0.0, 0.0, 0.0, ld_acquire_gpu(&sums[7])};
+      adam_bookkeeping(a, tstep, sv, take_best);
+      *ad.ticket = 0ull;
+    }
   }
 }
 
@@ -831,11 +907,13 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
-                          cudaStream_t st) {
+                          cudaStream_t st, const AdamParams* adam, unsigned long long* adam_ticket) {
+  AdamFuse ad{};
+  if (adam) { ad.on = 1; ad.a = *adam; ad.ticket = adam_ticket; }
   RedWeights wi{};
   if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
   return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS), dim3(RED_SLICES * 32), 0, st, partials, nrows, weights, wi, grad_mask, dtheta,
-                    sums, E_out, n, dp);
+                    sums, E_out, n, dp, ad);
 }
 
 }  // namespace pinn

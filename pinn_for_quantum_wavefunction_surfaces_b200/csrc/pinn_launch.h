@@ -88,8 +88,10 @@ struct DpArgs {
   unsigned char* peer[DP_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // exchange buffers, [rank] = own
 };
 // weights: device pointer, or NULL with weights_inline (host, 3 double) carried in the kernel parameters
+// adam (optional): the optimizer step of the device-resident trainer fused behind the reduction (pinn_train.h)
+struct AdamParams;
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
-                          cudaStream_t st);
+                          cudaStream_t st, const AdamParams* adam = nullptr, unsigned long long* adam_ticket = nullptr);
 
 }  // namespace pinn

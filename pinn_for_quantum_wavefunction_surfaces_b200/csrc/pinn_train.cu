@@ -28,56 +28,17 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }  // [0,1), 24 bits
 
-// One thread per point.  Point i of batch b uses counter (i_lo, i_hi, b_lo, b_hi) and key = seed; its four words give
-// x, y, z, R.  Clamp and sets follow the reference literally: both tests use the radii of the UN-clamped point
-// (train.py:32-35), the clamp writes the VALUE `cutoff` into x, and the sets are taken after it (train.py:36-39).
-__global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
-  pdl_wait();
-  const unsigned long long batch = *s.batch_counter;
-  unsigned c1 = 0, c2 = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
-    uint32_t r[4];
-    const unsigned long long gi = (unsigned long long)(i + s.index_offset);  // index of the point in the global batch
-    philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)batch, (uint32_t)(batch >> 32),
-                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32), r);
-    float x = fmaf(s.xR - s.xL, u01(r[0]), s.xL);
-    const float y = fmaf(s.yR - s.yL, u01(r[1]), s.yL);
-    const float z = fmaf(s.zR - s.zL, u01(r[2]), s.zL);
-    const float R = fmaf(s.RR - s.RL, u01(r[3]), s.RL);
-    const float yz = fmaf(y, y, z * z);
-    const float c2cut = s.cutoff * s.cutoff;
-    const bool near1 = fmaf(x - R, x - R, yz) < c2cut, near2 = fmaf(x + R, x + R, yz) < c2cut;
-    if (near1 || near2) x = s.cutoff;
-    const float b2 = s.bcutoff * s.bcutoff;
-    const unsigned m1 = fmaf(x - R, x - R, yz) >= b2, m2 = fmaf(x + R, x + R, yz) >= b2;
-    s.x[i] = x; s.y[i] = y; s.z[i] = z; s.R[i] = R;
-    s.mask[i] = (uint8_t)(m1 | (m2 << 1));
-    c1 += m1; c2 += m2;
-  }
-  c1 = __reduce_add_sync(0xffffffffu, c1);
-  c2 = __reduce_add_sync(0xffffffffu, c2);
-  __shared__ unsigned sh1[8], sh2[8];
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { sh1[w] = c1; sh2[w] = c2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t1 = 0, t2 = 0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { t1 += sh1[k]; t2 += sh2[k]; }
-    atomicAdd(&s.counts[0], (unsigned long long)t1);  // integer atomics: order-independent result
-    atomicAdd(&s.counts[1], (unsigned long long)t2);
-  }
-}
-
 // weights {1/n, 1/|set1|, 1/|set2|} of the reference's means (empty set -> inf -> NaN loss, as in the reference),
-// and the batch counter moves on.  One warp.  Data-parallel runs (dp.world > 1) first add the set sizes of all ranks:
+// and the batch counter moves on.  Run by one warp of the block of sample_kernel that finishes last.  Data-parallel runs (dp.world > 1) first add the set sizes of all ranks:
 // lane r stores this rank's two counts into peer r's exchange buffer as {count, step} words and polls its own buffer
 // for peer r's (same protocol as the gradient sum in reduce_partials_kernel), lane 0 adds them in rank order.
-__global__ void sample_finish_kernel(const unsigned long long* counts, long long n, double* w, unsigned long long* batch_counter,
-                                     const DpArgs dp) {
+__device__ __forceinline__ void sample_finish(const SampleParams& s) {
   __shared__ unsigned long long c[DP_MAX_WORLD][2];
+  const DpArgs& dp = s.dp;
   const int lane = threadIdx.x;
-  pdl_wait();
-  unsigned long long c1 = counts[0], c2 = counts[1];
+  const long long n = s.n;
+  double* w = s.weights;
+  unsigned long long c1 = atomicAdd(&s.counts[0], 0ull), c2 = atomicAdd(&s.counts[1], 0ull);  // L2 values of the other blocks' atomics
   long long ntot = n;
   if (dp.world > 1) {
     unsigned char* own = dp.peer[dp.rank];
@@ -117,18 +78,65 @@ __global__ void sample_finish_kernel(const unsigned long long* counts, long long
     w[0] = 1.0 / (double)ntot;
     w[1] = 1.0 / (double)c1;
     w[2] = 1.0 / (double)c2;
-    *batch_counter += 1ull;
+    *s.batch_counter += 1ull;
+    *s.ticket = 0ull;
+    if (s.reset_counts) { s.counts[0] = 0ull; s.counts[1] = 0ull; }
   }
 }
 
-cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& dp, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(s.counts, 0, 2 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return e;
+// One thread per point.  Point i of batch b uses counter (i_lo, i_hi, b_lo, b_hi) and key = seed; its four words give
+// x, y, z, R.  Clamp and sets follow the reference literally: both tests use the radii of the UN-clamped point
+// (train.py:32-35), the clamp writes the VALUE `cutoff` into x, and the sets are taken after it (train.py:36-39).
+__global__ void __launch_bounds__(256) sample_kernel(const SampleParams s) {
+  pdl_wait();
+  const unsigned long long batch = *s.batch_counter;
+  unsigned c1 = 0, c2 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    const unsigned long long gi = (unsigned long long)(i + s.index_offset);  // index of the point in the global batch
+    philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)batch, (uint32_t)(batch >> 32),
+                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32), r);
+    float x = fmaf(s.xR - s.xL, u01(r[0]), s.xL);
+    const float y = fmaf(s.yR - s.yL, u01(r[1]), s.yL);
+    const float z = fmaf(s.zR - s.zL, u01(r[2]), s.zL);
+    const float R = fmaf(s.RR - s.RL, u01(r[3]), s.RL);
+    const float yz = fmaf(y, y, z * z);
+    const float c2cut = s.cutoff * s.cutoff;
+    const bool near1 = fmaf(x - R, x - R, yz) < c2cut, near2 = fmaf(x + R, x + R, yz) < c2cut;
+    if (near1 || near2) x = s.cutoff;
+    const float b2 = s.bcutoff * s.bcutoff;
+    const unsigned m1 = fmaf(x - R, x - R, yz) >= b2, m2 = fmaf(x + R, x + R, yz) >= b2;
+    s.x[i] = x; s.y[i] = y; s.z[i] = z; s.R[i] = R;
+    s.mask[i] = (uint8_t)(m1 | (m2 << 1));
+    c1 += m1; c2 += m2;
+  }
+  c1 = __reduce_add_sync(0xffffffffu, c1);
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  __shared__ unsigned sh1[8], sh2[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh1[w] = c1; sh2[w] = c2; }
+  __syncthreads();
+  __shared__ int last_block;
+  if (threadIdx.x == 0) {
+    unsigned t1 = 0, t2 = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { t1 += sh1[k]; t2 += sh2[k]; }
+    atomicAdd(&s.counts[0], (unsigned long long)t1);  // integer atomics: order-independent result
+    atomicAdd(&s.counts[1], (unsigned long long)t2);
+    __threadfence();
+    last_block = atomicAdd(s.ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last_block && threadIdx.x < 32) sample_finish(s);  // every other block has added its counts and read the batch index
+}
+
+cudaError_t launch_sample(const SampleParams& s, bool zero_counts, cudaStream_t st) {
+  if (zero_counts) {
+    cudaError_t e = cudaMemsetAsync(s.counts, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+  }
   long long blocks = (s.n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  e = launch_pdl(sample_kernel, dim3((unsigned)blocks), dim3(256), 0, st, s);
-  if (e != cudaSuccess) return e;
-  return launch_pdl(sample_finish_kernel, dim3(1), dim3(32), 0, st, (const unsigned long long*)s.counts, s.n, weights, s.batch_counter, dp);
+  return launch_pdl(sample_kernel, dim3((unsigned)blocks), dim3(256), 0, st, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,50 +144,16 @@ cudaError_t launch_sample(const SampleParams& s, double* weights, const DpArgs& 
 // in float64, the reference's parameter dtype, plus best-model bookkeeping and history
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) adam_kernel(const AdamParams a) {
-  __shared__ int take_best;
+  __shared__ int take_best_s;
   pdl_wait();
   const unsigned long long t = *a.step;  // optimizer steps done so far = index tt of this step in the reference loops
-  const double Ltot = a.sums[0];
-  if (threadIdx.x == 0) {
-    bool tb;
-    if (a.best_mode == 0) tb = (t == 0ull) || (Ltot < *a.best_loss);              // train.py:58
-    else tb = ((double)t > a.best_after) && (Ltot < *a.best_loss);                // poc/main.py:414 (Llim starts at 10)
-    take_best = tb ? 1 : 0;
-    if (a.hist && (long long)t < a.hist_cap) {
-      double* h = a.hist + 4 * t;
-      h[0] = Ltot; h[1] = a.sums[1]; h[2] = a.sums[2];
-      h[3] = a.hist_mean_E ? a.sums[3] / (double)a.n : a.sums[7];  // train.py prints mean(e); poc keeps E[-1]
-    }
-  }
+  if (threadIdx.x == 0) take_best_s = adam_take_best(a, t, a.sums[0]) ? 1 : 0;
   __syncthreads();
-  const double tt = (double)(t + 1ull);
-  const double bc1 = 1.0 - pow(a.beta1, tt), bc2 = 1.0 - pow(a.beta2, tt);
-  const double step_size = a.lr / bc1, bc2_sqrt = sqrt(bc2);
-  const int offs[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
-                        O_WGL, O_BGL, O_WG, O_BG, NTHETA};
-  for (int i = threadIdx.x; i < NTHETA; i += blockDim.x) {
-    int ti = 0;
-#pragma unroll
-    for (int k = 1; k < 16; k++) ti += (i >= offs[k]);
-    double th = a.theta[i];
-    if (take_best && a.best_mode == 0) a.best_theta[i] = th;  // train.py keeps the parameters the loss was evaluated at
-    if ((a.grad_mask >> ti) & 1u) {                            // frozen tensors have no gradient: the optimizer skips them
-      const double g = a.grad[i];
-      double m = a.m[i], v = a.v[i];
-      m = m + (g - m) * (1.0 - a.beta1);
-      v = v * a.beta2 + ((1.0 - a.beta2) * g) * g;
-      const double denom = sqrt(v) / bc2_sqrt + a.eps;
-      th = th - step_size * (m / denom);
-      a.m[i] = m; a.v[i] = v; a.theta[i] = th;
-    }
-    if (take_best && a.best_mode == 1) a.best_theta[i] = th;  // poc saves the model after optimizer.step()
-    a.theta32[i] = (float)th;
-  }
+  const bool take_best = take_best_s != 0;
+  const AdamCoef c = adam_coef(a, t);
+  for (int i = threadIdx.x; i < NTHETA; i += blockDim.x) adam_update_entry(a, c, i, a.grad[i], take_best);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (take_best) { *a.best_loss = Ltot; *a.best_step = (long long)t; }
-    *a.step = t + 1ull;
-  }
+  if (threadIdx.x == 0) adam_bookkeeping(a, t, a.sums, take_best);
 }
 
 cudaError_t launch_adam(const AdamParams& a, cudaStream_t st) {

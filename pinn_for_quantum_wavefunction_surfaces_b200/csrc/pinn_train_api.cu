@@ -39,12 +39,11 @@ static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
     // ranks is exactly the batch a single GPU would draw for n_global = world*n
     const bool dp_run = h->dp_on && h->dp.world > 1;
     s.index_offset = dp_run ? (long long)h->dp.rank * c.n : 0;
-    CU(h, launch_sample(s, t->weights, dp_run ? h->dp : DpArgs(), st));
-    h->launches += 2;
+    s.weights = t->weights; s.ticket = t->counts + 2; s.reset_counts = 1;
+    if (dp_run) s.dp = h->dp;
+    CU(h, launch_sample(s, false, st));
+    h->launches += 1;
   }
-  int rc = pinn_loss_fwd_bwd(h, c.variant, c.n, t->x, t->y, t->z, t->R, PINN_F32, t->mask, t->theta32, t->weights,
-                             c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, (void*)st);
-  if (rc) return rc;
   AdamParams a{};
   a.theta = t->theta; a.m = t->m; a.v = t->v; a.grad = t->grad; a.sums = t->sums; a.theta32 = t->theta32;
   a.step = t->step; a.best_loss = t->best_loss; a.best_theta = t->best_theta; a.best_step = t->best_step;
@@ -52,8 +51,10 @@ static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
   a.n = c.n * ((h->dp_on && h->dp.world > 1) ? h->dp.world : 1);  // mean E of the history is over the global batch
   a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.eps; a.best_after = (double)c.best_after;
   a.grad_mask = c.grad_mask; a.best_mode = c.best_mode; a.hist_mean_E = c.history_mean_E;
-  CU(h, launch_adam(a, st));
-  h->launches += 1;
+  // the optimizer step rides in the reduction kernel: two launches per step (three with the sampler)
+  int rc = loss_fwd_bwd_impl(h, c.variant, c.n, t->x, t->y, t->z, t->R, PINN_F32, t->mask, t->theta32, t->weights, nullptr,
+                             nullptr, c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, st, &a, t->counts + 3);
+  if (rc) return rc;
   return 0;
 }
 
@@ -90,8 +91,9 @@ int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const 
   s.cutoff = cutoff; s.bcutoff = bcutoff;
   s.x = x; s.y = y; s.z = z; s.R = R; s.mask = mask; s.counts = (unsigned long long*)counts;
   s.index_offset = 0;
-  CU(h, launch_sample(s, weights, DpArgs(), st));
-  h->launches += 3;
+  s.weights = weights; s.ticket = h->batch_counter + 1; s.reset_counts = 0;
+  CU(h, launch_sample(s, true, st));
+  h->launches += 2;
   return 0;
 }
 
@@ -182,7 +184,7 @@ int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const doub
   TRAINER_CU(cudaMalloc(&t->x, n * 4)); TRAINER_CU(cudaMalloc(&t->y, n * 4)); TRAINER_CU(cudaMalloc(&t->z, n * 4));
   TRAINER_CU(cudaMalloc(&t->R, n * 4)); TRAINER_CU(cudaMalloc(&t->E, n * 4)); TRAINER_CU(cudaMalloc(&t->mask, n));
   TRAINER_CU(cudaMalloc(&t->theta32, NPART * 4));
-  TRAINER_CU(cudaMalloc(&t->counts, 16)); TRAINER_CU(cudaMalloc(&t->batch, 8)); TRAINER_CU(cudaMalloc(&t->step, 8)); TRAINER_CU(cudaMalloc(&t->best_step, 8));
+  TRAINER_CU(cudaMalloc(&t->counts, 32)); TRAINER_CU(cudaMemset(t->counts, 0, 32)); TRAINER_CU(cudaMalloc(&t->batch, 8)); TRAINER_CU(cudaMalloc(&t->step, 8)); TRAINER_CU(cudaMalloc(&t->best_step, 8));
   TRAINER_CU(cudaMalloc(&t->weights, 4 * 8));
   TRAINER_CU(cudaMalloc(&t->theta, NPART * 8)); TRAINER_CU(cudaMalloc(&t->m, NPART * 8)); TRAINER_CU(cudaMalloc(&t->v, NPART * 8));
   TRAINER_CU(cudaMalloc(&t->grad, NPART * 8)); TRAINER_CU(cudaMalloc(&t->sums, 8 * 8));
@@ -289,7 +291,7 @@ int pinn_trainer_run(pinn_trainer* t, int64_t steps, int resample, int use_graph
     const bool rs = resample && (tt % t->cfg.sc_sampling == 0) && (tt < t->cfg.freeze_after);
     if (use_graph) {
       CU(h, cudaGraphLaunch(rs ? t->g_resample : t->g_keep, t->st));
-      h->launches += rs ? 7 : 5;
+      h->launches += rs ? 3 : 2;
     } else {
       int rc = trainer_enqueue(t, rs, t->st);
       if (rc) return rc;
