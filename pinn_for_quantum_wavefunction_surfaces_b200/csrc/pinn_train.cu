@@ -135,7 +135,7 @@ cudaError_t launch_sample(const SampleParams& s, bool zero_counts, cudaStream_t 
     if (e != cudaSuccess) return e;
   }
   long long blocks = (s.n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;  // two waves of 256 threads per SM: ~3.5 points per thread at 2^18, few blocks to launch and to count
   return launch_pdl(sample_kernel, dim3((unsigned)blocks), dim3(256), 0, st, s);
 }
 
