@@ -107,6 +107,52 @@ __device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col
   weighted = t0 + t1;
 }
 
+// Packed column sums (FADD2 / FFMA2: half the instructions of the scalar versions above).  Lane = 16 * half + pair
+// sums the 16 rows [16 half, 16 half + 16) of the two adjacent columns col2, col2 + 1 (col2 even).  The two halves are
+// separate accumulators until the kernel's final fold.
+template <int ROW>
+__device__ __forceinline__ float2 colsum2(const float* __restrict__ base, int col2, int half) {
+  const float* b = base + half * 16 * ROW;
+  const float2* p0 = reinterpret_cast<const float2*>(b + col2);
+  const float2* p1 = reinterpret_cast<const float2*>(b + ROW + (col2 ^ 8));
+  const float2* p2 = reinterpret_cast<const float2*>(b + 2 * ROW + (col2 ^ 16));
+  const float2* p3 = reinterpret_cast<const float2*>(b + 3 * ROW + (col2 ^ 24));
+  float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int p = 0; p < 16; p += 4) {
+    s0 = __fadd2_rn(s0, p0[p * (ROW / 2)]);
+    s1 = __fadd2_rn(s1, p1[p * (ROW / 2)]);
+    s0 = __fadd2_rn(s0, p2[p * (ROW / 2)]);
+    s1 = __fadd2_rn(s1, p3[p * (ROW / 2)]);
+  }
+  return __fadd2_rn(s0, s1);
+}
+// ... and with per-row weights: plain = sum_p v[p][.], weighted = sum_p wgt_p v[p][.] (wgt = the value lane p holds)
+template <int ROW>
+__device__ __forceinline__ void colsum2_w(const float* __restrict__ base, int col2, int half, float wgt, float2& plain,
+                                          float2& weighted) {
+  const float* b = base + half * 16 * ROW;
+  const float2* p0 = reinterpret_cast<const float2*>(b + col2);
+  const float2* p1 = reinterpret_cast<const float2*>(b + ROW + (col2 ^ 8));
+  const float2* p2 = reinterpret_cast<const float2*>(b + 2 * ROW + (col2 ^ 16));
+  const float2* p3 = reinterpret_cast<const float2*>(b + 3 * ROW + (col2 ^ 24));
+  float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, t0 = s0, t1 = s0;
+  const int r0 = half * 16;
+#pragma unroll
+  for (int p = 0; p < 16; p += 4) {
+    const float2 v0 = p0[p * (ROW / 2)], v1 = p1[p * (ROW / 2)], v2 = p2[p * (ROW / 2)], v3 = p3[p * (ROW / 2)];
+    const float w0 = __shfl_sync(0xffffffffu, wgt, r0 + p + 0), w1 = __shfl_sync(0xffffffffu, wgt, r0 + p + 1);
+    const float w2 = __shfl_sync(0xffffffffu, wgt, r0 + p + 2), w3 = __shfl_sync(0xffffffffu, wgt, r0 + p + 3);
+    s0 = __fadd2_rn(s0, v0); s1 = __fadd2_rn(s1, v1); s0 = __fadd2_rn(s0, v2); s1 = __fadd2_rn(s1, v3);
+    t0 = __ffma2_rn(v0, make_float2(w0, w0), t0);
+    t1 = __ffma2_rn(v1, make_float2(w1, w1), t1);
+    t0 = __ffma2_rn(v2, make_float2(w2, w2), t0);
+    t1 = __ffma2_rn(v3, make_float2(w3, w3), t1);
+  }
+  plain = __fadd2_rn(s0, s1);
+  weighted = __fadd2_rn(t0, t1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-point geometry (poc/main.py:101-108, 269-284; train.py:41-44) and the coefficients of the
 // second-order operator D (oracle/closed_form.py:geometry)

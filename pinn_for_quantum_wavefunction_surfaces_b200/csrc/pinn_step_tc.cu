@@ -245,10 +245,13 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
 //               s2: lane<16 db1[lane] | extra[lane-16] (loss sums, role 0)
 //   E-net warp: c[mt][nt] = C fragments of dWE2 (32x32);
 //               s0..s4 = dwE[lane], dbE2[lane], dWE1[lane], dbE1[lane], {dWgL,dbgL,dwg,dbg,dbE}[lane]
+// The vector sums are packed pairs (colsum2): lane = 16 * half + pair holds, for the two columns 2 pair, 2 pair + 1 of the
+// 32-column window of s_k, the sum over the rows of its half; the halves are added in the final fold.
 struct TcAcc {
   float c[2][4][4];
-  float s0, s1, s2, s3, s4;
+  float2 s0, s1, s2, s3, s4;
 };
+__device__ __forceinline__ void acc2(float2& a, const float2 v) { a = __fadd2_rn(a, v); }
 using TcMlpAcc = TcAcc;
 using TcEnetAcc = TcAcc;
 
@@ -346,7 +349,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   for (int j4 = 0; j4 < NH; j4 += 4) ST4(&Grow[(NH + j4) ^ sx], dwo[j4], dwo[j4 + 1], dwo[j4 + 2], dwo[j4 + 3]);
   __syncwarp();
   TL(9);
-  acc.s0 += colsum<ROWH>(Gs, lane);
+  acc2(acc.s0, colsum2<ROWH>(Gs, 2 * (lane & 15), lane >> 4));
 
   // ---- hbar = W2^T vbar is in TMEM now: layer-1 reverse sweep ----
   TL(10);
@@ -395,8 +398,8 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
   __syncwarp();
   TL(12);
-  acc.s1 += colsum<ROWH>(Hs, NH + lane);                              // columns 16..47: dw0 | dw1
-  acc.s2 += colsum<ROWH>(Hs, lane < 16 ? 3 * NH + lane : lane - 16);  // columns 48..63: db1 ; 0..15: extras
+  acc2(acc.s1, colsum2<ROWH>(Hs, NH + 2 * (lane & 15), lane >> 4));               // columns 16..47: dw0 | dw1
+  acc2(acc.s2, colsum2<ROWH>(Hs, (3 * NH + 2 * (lane & 15)) & 63, lane >> 4));    // columns 48..63: db1 ; 0..15: extras
   __syncwarp();
 }
 
@@ -408,8 +411,8 @@ __device__ __forceinline__ void tc_mlp_extras_only(float* __restrict__ Hs, int l
   ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
   ST4(&Hrow[4 ^ sx], extra[4], extra[5], extra[6], extra[7]);
   __syncwarp();
-  const float v = colsum<ROWH>(Hs, lane & 7);
-  if (lane >= 16 && lane < 24) acc.s2 += v;
+  const float2 v = colsum2<ROWH>(Hs, (3 * NH + 2 * (lane & 15)) & 63, lane >> 4);  // same window as in tc_mlp_backward
+  if ((lane & 15) >= 8 && (lane & 15) < 12) acc2(acc.s2, v);                       // its columns 0..7: the extras
   __syncwarp();
 }
 
@@ -488,9 +491,9 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   __syncwarp();
   // ---- dwE[j] = sum_p Ebar_p e2[p][j] (Vs still holds e2) ----
   {
-    float plain, weighted;
-    colsum_w<ROWE>(Vs, lane, Ebar, plain, weighted);
-    acc.s0 += weighted;
+    float2 plain, weighted;
+    colsum2_w<ROWE>(Vs, 2 * (lane & 15), lane >> 4, Ebar, plain, weighted);
+    acc2(acc.s0, weighted);
   }
   __syncwarp();
 #pragma unroll
@@ -548,7 +551,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
     }
   }
   TL(9);
-  acc.s1 += colsum<ROWE>(Vs, lane);  // dbE2
+  acc2(acc.s1, colsum2<ROWE>(Vs, 2 * (lane & 15), lane >> 4));  // dbE2
   __syncwarp();                      // Vs rows may now be overwritten
   // ---- e1bar = WE2^T vbar is in TMEM: layer-1 reverse sweep; ubar_k -> Vs row ----
   TL(10);
@@ -587,12 +590,12 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   }
   __syncwarp();
   {
-    float plain, weighted;
-    colsum_w<ROWE>(Vs, lane, R, plain, weighted);
-    acc.s2 += weighted;  // dWE1[k] = sum_p ubar_k R_p
-    acc.s3 += plain;     // dbE1
+    float2 plain, weighted;
+    colsum2_w<ROWE>(Vs, 2 * (lane & 15), lane >> 4, R, plain, weighted);
+    acc2(acc.s2, weighted);  // dWE1[k] = sum_p ubar_k R_p
+    acc2(acc.s3, plain);     // dbE1
   }
-  acc.s4 += colsum<ROWE>(E1s, lane);
+  acc2(acc.s4, colsum2<ROWE>(E1s, 2 * (lane & 15), lane >> 4));
   __syncwarp();
 }
 
@@ -600,6 +603,18 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
 // the fused kernel.  NEV = MLP evaluations per point (2: poc, 1: train.py); TRAIN = with reverse sweep
 //   warp = role * 4 + group;  role < NEV: MLP evaluation, role == NEV: E-net + gate
 // ---------------------------------------------------------------------------------------------
+// final fold of a packed vector sum: add the two row halves (lanes l and l + 16), lanes 0..15 store their two columns
+template <typename EntryOf>
+__device__ __forceinline__ void fold_pair(float* __restrict__ myrow, float2 v, int lane, EntryOf entry_of) {
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+  v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+  if (lane < 16) {
+    const int a = entry_of(2 * lane), b = entry_of(2 * lane + 1);
+    if (a >= 0) myrow[a] = v.x;
+    if (b >= 0) myrow[b] = v.y;
+  }
+}
+
 // Kernel parameters: the launch description; the INLINE instantiations (the *_host entry) also carry theta and the loss
 // weights by value (6 KB of parameter space; sm_100 takes up to 32 KB), so that no host-to-device copy has to precede
 // the kernel.
@@ -727,7 +742,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     for (int b = 0; b < 4; b++)
 #pragma unroll
       for (int cc = 0; cc < 4; cc++) acc.c[a][b][cc] = 0.0f;
-  acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = 0.0f;
+  acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = make_float2(0.0f, 0.0f);
 
   double gs0 = 0.0, gs1 = 0.0, gs2 = 0.0, gs3 = 0.0, gs4 = 0.0;  // dense-grid quadrature sums (role 0, inference only)
 
@@ -913,15 +928,19 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2];
         myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3];
       }
-      myrow[lane < 16 ? O_B2 + lane : O_WO + lane - 16] = acc.s0;
-      myrow[lane < 16 ? O_W1 + 2 * lane : O_W1 + 2 * (lane - 16) + 1] = acc.s1;
-      if (lane < 16) myrow[O_B1 + lane] = acc.s2;
-      else if (role == 0) {
-        const int e = lane - 16;
-        const int dst = e == 0 ? S_RES2 : e == 1 ? S_PSI1 : e == 2 ? S_PSI2 : e == 3 ? S_E
-                      : e == 4 ? O_BO : e == 5 ? S_CNT1 : e == 6 ? S_CNT2 : -1;
-        if (dst >= 0) myrow[dst] = acc.s2;
-      }
+      // window index i (0..31) of each vector sum -> entry of the row
+      auto e0 = [](int i) { return i < 16 ? O_B2 + i : O_WO + i - 16; };
+      auto e1 = [](int i) { return i < 16 ? O_W1 + 2 * i : O_W1 + 2 * (i - 16) + 1; };
+      auto e2 = [role](int i) {
+        if (i < 16) return (int)O_B1 + i;
+        if (role != 0) return -1;
+        const int e = i - 16;
+        return e == 0 ? (int)S_RES2 : e == 1 ? (int)S_PSI1 : e == 2 ? (int)S_PSI2 : e == 3 ? (int)S_E
+             : e == 4 ? (int)O_BO : e == 5 ? (int)S_CNT1 : e == 6 ? (int)S_CNT2 : -1;
+      };
+      fold_pair(myrow, acc.s0, lane, e0);
+      fold_pair(myrow, acc.s1, lane, e1);
+      fold_pair(myrow, acc.s2, lane, e2);
     } else {
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
@@ -933,13 +952,13 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
           myrow[O_WE2 + (j + 8) * NE + k] = acc.c[mt][nt][2];
           myrow[O_WE2 + (j + 8) * NE + k + 1] = acc.c[mt][nt][3];
         }
-      myrow[O_WE + lane] = acc.s0;
-      myrow[O_BE2 + lane] = acc.s1;
-      myrow[O_WE1 + lane] = acc.s2;
-      myrow[O_BE1 + lane] = acc.s3;
-      const int dst = lane < 10 ? O_WGL + lane : lane < 20 ? O_BGL + lane - 10 : lane < 30 ? O_WG + lane - 20
-                    : lane == 30 ? O_BG : O_BE;
-      myrow[dst] = acc.s4;
+      fold_pair(myrow, acc.s0, lane, [](int i) { return (int)O_WE + i; });
+      fold_pair(myrow, acc.s1, lane, [](int i) { return (int)O_BE2 + i; });
+      fold_pair(myrow, acc.s2, lane, [](int i) { return (int)O_WE1 + i; });
+      fold_pair(myrow, acc.s3, lane, [](int i) { return (int)O_BE1 + i; });
+      fold_pair(myrow, acc.s4, lane, [](int i) {
+        return i < 10 ? (int)O_WGL + i : i < 20 ? (int)O_BGL + i - 10 : i < 30 ? (int)O_WG + i - 20 : i == 30 ? (int)O_BG : (int)O_BE;
+      });
     }
   }
   __syncthreads();

@@ -1,5 +1,6 @@
+"""Python-side overhead of the prepared host call (HostStep) on top of pinn_loss_fwd_bwd_host."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pinn_for_quantum_wavefunction_surfaces_b200 as pk
 import bench
 n = 1 << 18

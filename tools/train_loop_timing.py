@@ -1,5 +1,6 @@
+"""Device-resident training loop (pinn_trainer): time per optimizer step, CUDA-graph replay vs plain launches."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pinn_for_quantum_wavefunction_surfaces_b200 as pk
 import bench
 n = 1 << 18
