@@ -336,10 +336,12 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
         uint32_t bh0, bl0, bh1, bl1;
         split_tf32(Ha[ca], bh0, bl0);
         split_tf32(Hb[ca], bh1, bl1);
-        mma_3xtf32(acc.c[0][0], ah, al, bh0, bh1, bl0, bl1);
+        // even / odd k-steps accumulate into separate fragments: four independent HMMA chains instead of two (the
+        // phase is bound by the accumulate latency of the legacy tensor path, not by its throughput)
+        mma_3xtf32(acc.c[po & 1][0], ah, al, bh0, bh1, bl0, bl1);
         split_tf32(Ha[cbb], bh0, bl0);
         split_tf32(Hb[cbb], bh1, bl1);
-        mma_3xtf32(acc.c[0][1], ah, al, bh0, bh1, bl0, bl1);
+        mma_3xtf32(acc.c[po & 1][1], ah, al, bh0, bh1, bl0, bl1);
       }
     }
   }
@@ -923,10 +925,10 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     if (is_mlp) {
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) {
-        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0];
-        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1];
-        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2];
-        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3];
+        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0] + acc.c[1][nt][0];
+        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1] + acc.c[1][nt][1];
+        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2] + acc.c[1][nt][2];
+        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3] + acc.c[1][nt][3];
       }
       // window index i (0..31) of each vector sum -> entry of the row
       auto e0 = [](int i) { return i < 16 ? O_B2 + i : O_WO + i - 16; };
