@@ -620,6 +620,9 @@ __device__ __forceinline__ void fold_pair(float* __restrict__ myrow, float2 v, i
 // Kernel parameters: the launch description; the INLINE instantiations (the *_host entry) also carry theta and the loss
 // weights by value (6 KB of parameter space; sm_100 takes up to 32 KB), so that no host-to-device copy has to precede
 // the kernel.
+constexpr int TC_REG_MLP = 184, TC_REG_ENET = 136;  // setmaxnreg targets of the poc training kernel (see the kernel's tail)
+static_assert(128 * TC_REG_ENET + 256 * TC_REG_MLP <= 384 * 168, "register rebalancing must fit the launch allocation");
+
 struct TcParamsPlain {
   StepParams p;
 };
@@ -714,265 +717,279 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     __syncthreads();
   }
 
-  TcCtx c;
-  c.tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  c.tlane = c.tbase + ((uint32_t)(grp * 32) << 16);
-  c.mbar = smem_u32(&mbars[1 + role]);
-  c.phase = 0;
-  c.bar_id = 5 + role;
-  c.issuer = (grp == 0);
-  c.wts_saddr = smem_u32(&w);
-  const uint32_t cb = is_mlp ? (uint32_t)role * TC_MLP_COLS : TC_E_BASE;
+  // The rest of the kernel is instantiated once per kind of role, in two disjoint branches: with the role a compile-time
+  // constant each branch only contains its own code, and (poc training kernel) the branches start with setmaxnreg so
+  // that the two MLP warpgroups take over the registers the E-net warpgroup does not need.
+  auto run_role = [&](auto mlp_tag) {
+    constexpr bool IS_MLP = decltype(mlp_tag)::value;
+    TcCtx c;
+    c.tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    c.tlane = c.tbase + ((uint32_t)(grp * 32) << 16);
+    c.mbar = smem_u32(&mbars[1 + role]);
+    c.phase = 0;
+    c.bar_id = 5 + role;
+    c.issuer = (grp == 0);
+    c.wts_saddr = smem_u32(&w);
+    const uint32_t cb = IS_MLP ? (uint32_t)role * TC_MLP_COLS : TC_E_BASE;
 
-  float* gstash = stash + grp * tc_group_stash_floats<NEV>();
-  float* Hs = gstash + (is_mlp ? role * EVAL_STASH : NEV * EVAL_STASH);
-  float* Gs = Hs + (is_mlp ? 32 * ROWH : 32 * ROWE);  // for the E-net warp: Hs = E1s, Gs = Vs
-  float2* gbox = mbox + grp * (2 * 3 * 32);
+    float* gstash = stash + grp * tc_group_stash_floats<NEV>();
+    float* Hs = gstash + (IS_MLP ? role * EVAL_STASH : NEV * EVAL_STASH);
+    float* Gs = Hs + (IS_MLP ? 32 * ROWH : 32 * ROWE);  // for the E-net warp: Hs = E1s, Gs = Vs
+    float2* gbox = mbox + grp * (2 * 3 * 32);
 
-  double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
-  if (TRAIN) {
-    if constexpr (INLINE) { wpde = q.w[0]; wbc1 = q.w[1]; wbc2 = q.w[2]; }
-    else { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
-  }
-  const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
-  const float sN = p.vc.sN, cL = p.vc.cL, cV = p.vc.cV, cE = p.vc.cE;
-
-  TcAcc acc;
-#pragma unroll
-  for (int a = 0; a < 2; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++) acc.c[a][b][cc] = 0.0f;
-  acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = make_float2(0.0f, 0.0f);
-
-  double gs0 = 0.0, gs1 = 0.0, gs2 = 0.0, gs3 = 0.0, gs4 = 0.0;  // dense-grid quadrature sums (role 0, inference only)
-
-  // every warp of the CTA walks the same super-tiles (the role barriers need all 4 groups); groups whose
-  // 32 points lie beyond n compute on a clamped index with zero weight
-  const long long nsuper = (p.n + 127) >> 7;
-  int it = 0;
-  if (stager) cp_async_wait_next();  // the first super-tile's coordinates (requested before the weight image was built)
-  __syncthreads();
-  TLK(1);
-  for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
-    const long long pidx = st * 128 + slot;
-    const bool valid = pidx < p.n;
-    const long long pi = valid ? pidx : (p.n - 1);
-    c.tl_it = it;
-    TL(0);
-    if (it < 38) TLK(2 + it);
-    const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
-    const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
-    const Geom g = geom_from_raw(raw);
-    const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
-    if (stager) {  // coordinates COORD_AHEAD super-tiles ahead: in flight while this one (and the next) is computed
-      const long long in = pidx + (long long)COORD_AHEAD * gridDim.x * 128;
-      if (st + (long long)COORD_AHEAD * gridDim.x < nsuper)
-        coord_stage_issue(p, cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
-      cp_async_commit();
+    double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
+    if (TRAIN) {
+      if constexpr (INLINE) { wpde = q.w[0]; wbc1 = q.w[1]; wbc2 = q.w[2]; }
+      else { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
     }
-    float2* box = gbox + (it & 1) * (3 * 32);
+    const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
+    const float sN = p.vc.sN, cL = p.vc.cL, cV = p.vc.cV, cE = p.vc.cE;
 
-    // the evaluation at the inversion image swaps the roles of the two nuclei (poc/main.py:255-256)
-    const bool sw = (role == 1) && is_mlp;
-    const float a = sw ? g.f2 : g.f1, b = sw ? g.f1 : g.f2;
-    const float al1 = sw ? g.al2 : g.al1, al2 = sw ? g.al1 : g.al2;
-    const float al11 = sw ? g.al22 : g.al11, al22 = sw ? g.al11 : g.al22;
-    const float al12 = g.al12;
+    TcAcc acc;
+  #pragma unroll
+    for (int a = 0; a < 2; a++)
+  #pragma unroll
+      for (int b = 0; b < 4; b++)
+  #pragma unroll
+        for (int cc = 0; cc < 4; cc++) acc.c[a][b][cc] = 0.0f;
+    acc.s0 = acc.s1 = acc.s2 = acc.s3 = acc.s4 = make_float2(0.0f, 0.0f);
 
-    if (is_mlp) {
-      float Nv, Dv;
-      tc_mlp_forward<TRAIN>(w, c, cb, a, b, al1, al2, al11, al12, al22, Hs + lane * ROWH, Gs + lane * ROWH, sx, Nv, Dv);
-      box[role * 32 + lane] = make_float2(Nv, Dv);
-    } else {
-      const float E = tc_enet_forward<TRAIN>(w, c, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx);
-      const float gt = tc_gate_forward(w, g.R);
-      box[2 * 32 + lane] = make_float2(E, gt);
-    }
-    TL(5);
-    if (stager) cp_async_wait_next();  // the NEXT tile's coordinates have landed; the barrier publishes them to the group
-    named_barrier(1 + grp, (NEV + 1) * 32);
-    TL(6);
+    double gs0 = 0.0, gs1 = 0.0, gs2 = 0.0, gs3 = 0.0, gs4 = 0.0;  // dense-grid quadrature sums (role 0, inference only)
 
-    // ---- combine (every role recomputes the few scalars it needs) ----
-    float2 m0 = box[lane];
-    if (NEV == 2) { const float2 m1 = box[32 + lane]; m0.x += m1.x; m0.y += m1.y; }
-    const float2 me = box[2 * 32 + lane];
-    const float E = me.x, gate = me.y;
-    const float N = fmaf(sN, m0.x, w.bo), DN = sN * m0.y;
-    const float q = g.ir1 + g.ir2;
-    const float fs = g.f1 + g.f2;
-    const float psi = fmaf(gate, N, fs);
-    const float lcao = fmaf(cL, fs, fmaf(cV - 2.0f * cL, fmaf(g.f1, g.ir1, g.f2 * g.ir2),
-                                          cV * fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
-    const float inner = fmaf(cL, DN, cV * q * N);
-    const float res = fmaf(gate, inner, fmaf(cE * E, psi, lcao));
+    // every warp of the CTA walks the same super-tiles (the role barriers need all 4 groups); groups whose
+    // 32 points lie beyond n compute on a clamped index with zero weight
+    const long long nsuper = (p.n + 127) >> 7;
+    int it = 0;
+    if (stager) cp_async_wait_next();  // the first super-tile's coordinates (requested before the weight image was built)
+    __syncthreads();
+    TLK(1);
+    for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
+      const long long pidx = st * 128 + slot;
+      const bool valid = pidx < p.n;
+      const long long pi = valid ? pidx : (p.n - 1);
+      c.tl_it = it;
+      TL(0);
+      if (it < 38) TLK(2 + it);
+      const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
+      const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
+      const Geom g = geom_from_raw(raw);
+      const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
+      if (stager) {  // coordinates COORD_AHEAD super-tiles ahead: in flight while this one (and the next) is computed
+        const long long in = pidx + (long long)COORD_AHEAD * gridDim.x * 128;
+        if (st + (long long)COORD_AHEAD * gridDim.x < nsuper)
+          coord_stage_issue(p, cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
+        cp_async_commit();
+      }
+      float2* box = gbox + (it & 1) * (3 * 32);
 
-    if (!TRAIN) {
-      if (p.grid.on) {
-        if (valid && role == 0) {
-          int ix, iy, iz;
-          grid_ijk(p.grid, pidx, ix, iy, iz);
-          const double wq = p.grid.wx[ix] * p.grid.wy[iy] * p.grid.wz[iz];
-          // Hartree form of H psi (poc/main.py:118-120) with the cusp terms cancelled analytically, and its LCAO part
-          const float hl = fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1));
-          const float hpsi = fmaf(gate, fmaf(-0.5f, DN, -q * N), hl);
-          // dV/dR = -(x-R)/r1^3 + (x+R)/r2^3 (poc/main.py:637-642)
-          const float vr = fmaf(-cur_dx1, g.ir1 * g.ir1 * g.ir1, cur_dx2 * g.ir2 * g.ir2 * g.ir2);
-          gs0 += wq * (double)(psi * hpsi);
-          gs1 += wq * (double)(psi * psi);
-          gs2 += wq * (double)(fs * hl);
-          gs3 += wq * (double)(fs * fs);
-          gs4 += wq * (double)(vr * psi * psi);
-        } else if (!is_mlp && st == 0 && grp == 0 && lane == 0) {
-          p.grid.partials[8 * (size_t)gridDim.x] = (double)E;  // E(R) of the launch, behind the partial rows
+      // the evaluation at the inversion image swaps the roles of the two nuclei (poc/main.py:255-256)
+      const bool sw = (role == 1) && IS_MLP;
+      const float a = sw ? g.f2 : g.f1, b = sw ? g.f1 : g.f2;
+      const float al1 = sw ? g.al2 : g.al1, al2 = sw ? g.al1 : g.al2;
+      const float al11 = sw ? g.al22 : g.al11, al22 = sw ? g.al11 : g.al22;
+      const float al12 = g.al12;
+
+      if (IS_MLP) {
+        float Nv, Dv;
+        tc_mlp_forward<TRAIN>(w, c, cb, a, b, al1, al2, al11, al12, al22, Hs + lane * ROWH, Gs + lane * ROWH, sx, Nv, Dv);
+        box[role * 32 + lane] = make_float2(Nv, Dv);
+      } else {
+        const float E = tc_enet_forward<TRAIN>(w, c, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx);
+        const float gt = tc_gate_forward(w, g.R);
+        box[2 * 32 + lane] = make_float2(E, gt);
+      }
+      TL(5);
+      if (stager) cp_async_wait_next();  // the NEXT tile's coordinates have landed; the barrier publishes them to the group
+      named_barrier(1 + grp, (NEV + 1) * 32);
+      TL(6);
+
+      // ---- combine (every role recomputes the few scalars it needs) ----
+      float2 m0 = box[lane];
+      if (NEV == 2) { const float2 m1 = box[32 + lane]; m0.x += m1.x; m0.y += m1.y; }
+      const float2 me = box[2 * 32 + lane];
+      const float E = me.x, gate = me.y;
+      const float N = fmaf(sN, m0.x, w.bo), DN = sN * m0.y;
+      const float q = g.ir1 + g.ir2;
+      const float fs = g.f1 + g.f2;
+      const float psi = fmaf(gate, N, fs);
+      const float lcao = fmaf(cL, fs, fmaf(cV - 2.0f * cL, fmaf(g.f1, g.ir1, g.f2 * g.ir2),
+                                            cV * fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+      const float inner = fmaf(cL, DN, cV * q * N);
+      const float res = fmaf(gate, inner, fmaf(cE * E, psi, lcao));
+
+      if (!TRAIN) {
+        if (p.grid.on) {
+          if (valid && role == 0) {
+            int ix, iy, iz;
+            grid_ijk(p.grid, pidx, ix, iy, iz);
+            const double wq = p.grid.wx[ix] * p.grid.wy[iy] * p.grid.wz[iz];
+            // Hartree form of H psi (poc/main.py:118-120) with the cusp terms cancelled analytically, and its LCAO part
+            const float hl = fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1));
+            const float hpsi = fmaf(gate, fmaf(-0.5f, DN, -q * N), hl);
+            // dV/dR = -(x-R)/r1^3 + (x+R)/r2^3 (poc/main.py:637-642)
+            const float vr = fmaf(-cur_dx1, g.ir1 * g.ir1 * g.ir1, cur_dx2 * g.ir2 * g.ir2 * g.ir2);
+            gs0 += wq * (double)(psi * hpsi);
+            gs1 += wq * (double)(psi * psi);
+            gs2 += wq * (double)(fs * hl);
+            gs3 += wq * (double)(fs * fs);
+            gs4 += wq * (double)(vr * psi * psi);
+          } else if (!IS_MLP && st == 0 && grp == 0 && lane == 0) {
+            p.grid.partials[8 * (size_t)gridDim.x] = (double)E;  // E(R) of the launch, behind the partial rows
+          }
+          continue;
+        }
+        if (valid) {
+          if (role == 0) {
+            if (p.psi) p.psi[pidx] = psi;
+            if (p.lap) p.lap[pidx] = g.al1 + g.al2 + gate * DN;
+            if (p.res) p.res[pidx] = res;
+            if (p.hpsi)
+              p.hpsi[pidx] = fmaf(gate, fmaf(-0.5f, DN, -q * N),
+                                  fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
+          } else if (!IS_MLP) {
+            if (p.E_out) p.E_out[pidx] = E;
+          }
         }
         continue;
       }
-      if (valid) {
+
+      // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
+      float m1f, m2f;
+      if (p.mask) {
+        const unsigned mk = *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
+        m1f = (mk & 1u) ? 1.0f : 0.0f;
+        m2f = (mk & 2u) ? 1.0f : 0.0f;
+      } else {
+        m1f = (g.ir1 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+        m2f = (g.ir2 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+      }
+      const float vw = valid ? 1.0f : 0.0f;
+      const float rbar = 2.0f * w_pde * res * vw;
+      const float pbar = 2.0f * fmaf(w_bc1, m1f, w_bc2 * m2f) * psi * vw;
+      if (IS_MLP) {
+        const float lamN = fmaf(rbar, gate * fmaf(cV, q, cE * E), pbar * gate);
+        const float lamD = rbar * cL * gate;
+        float extra[8];
+  #pragma unroll
+        for (int i = 0; i < 8; i++) extra[i] = 0.0f;
         if (role == 0) {
-          if (p.psi) p.psi[pidx] = psi;
-          if (p.lap) p.lap[pidx] = g.al1 + g.al2 + gate * DN;
-          if (p.res) p.res[pidx] = res;
-          if (p.hpsi)
-            p.hpsi[pidx] = fmaf(gate, fmaf(-0.5f, DN, -q * N),
-                                fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
-        } else if (!is_mlp) {
-          if (p.E_out) p.E_out[pidx] = E;
+          extra[0] = res * res * vw;
+          extra[1] = psi * psi * m1f * vw;
+          extra[2] = psi * psi * m2f * vw;
+          extra[3] = E * vw;
+          extra[4] = p.base_grads ? lamN : 0.0f;  // dL/dbo
+          extra[5] = m1f * vw;
+          extra[6] = m2f * vw;
         }
+        if (p.base_grads) {
+          tc_mlp_backward(w, c, cb, a, b, al1, al2, al11, al12, al22, sN * lamN, sN * lamD, Hs, Gs, lane, extra, acc);
+        } else if (role == 0) {
+          tc_mlp_extras_only(Hs, lane, extra, acc);
+        }
+      } else {
+        if (valid && p.E_out) p.E_out[pidx] = E;
+        const float gbar = fmaf(rbar, fmaf(cE * E, N, inner), pbar * N);
+        const float Ebar = rbar * cE * psi;
+        tc_enet_backward(w, c, g.R, Ebar, gbar, p.gate_grads != 0, Hs, Gs, lane, acc);
       }
-      continue;
+      TL(15);
     }
 
-    // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
-    float m1f, m2f;
-    if (p.mask) {
-      const unsigned mk = *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
-      m1f = (mk & 1u) ? 1.0f : 0.0f;
-      m2f = (mk & 2u) ? 1.0f : 0.0f;
-    } else {
-      m1f = (g.ir1 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
-      m2f = (g.ir2 * p.bcut <= 1.0f) ? 1.0f : 0.0f;
+    TLK(40);
+    // the reduction kernel behind this launch may be set up now (it waits for this grid to complete before it reads)
+    pdl_launch_dependents();
+    // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(c.tbase) : "memory");
     }
-    const float vw = valid ? 1.0f : 0.0f;
-    const float rbar = 2.0f * w_pde * res * vw;
-    const float pbar = 2.0f * fmaf(w_bc1, m1f, w_bc2 * m2f) * psi * vw;
-    if (is_mlp) {
-      const float lamN = fmaf(rbar, gate * fmaf(cV, q, cE * E), pbar * gate);
-      const float lamD = rbar * cL * gate;
-      float extra[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) extra[i] = 0.0f;
-      if (role == 0) {
-        extra[0] = res * res * vw;
-        extra[1] = psi * psi * m1f * vw;
-        extra[2] = psi * psi * m2f * vw;
-        extra[3] = E * vw;
-        extra[4] = p.base_grads ? lamN : 0.0f;  // dL/dbo
-        extra[5] = m1f * vw;
-        extra[6] = m2f * vw;
-      }
-      if (p.base_grads) {
-        tc_mlp_backward(w, c, cb, a, b, al1, al2, al11, al12, al22, sN * lamN, sN * lamD, Hs, Gs, lane, extra, acc);
-      } else if (role == 0) {
-        tc_mlp_extras_only(Hs, lane, extra, acc);
-      }
-    } else {
-      if (valid && p.E_out) p.E_out[pidx] = E;
-      const float gbar = fmaf(rbar, fmaf(cE * E, N, inner), pbar * N);
-      const float Ebar = rbar * cE * psi;
-      tc_enet_backward(w, c, g.R, Ebar, gbar, p.gate_grads != 0, Hs, Gs, lane, acc);
-    }
-    TL(15);
-  }
-
-  TLK(40);
-  // the reduction kernel behind this launch may be set up now (it waits for this grid to complete before it reads)
-  pdl_launch_dependents();
-  // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(c.tbase) : "memory");
-  }
-  if (!TRAIN) {
-    if (p.grid.on) {  // one row of quadrature sums per CTA, fixed order
-      double* red = reinterpret_cast<double*>(stash);
-      if (role == 0) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gs1 += __shfl_xor_sync(0xffffffffu, gs1, o);
-          gs2 += __shfl_xor_sync(0xffffffffu, gs2, o); gs3 += __shfl_xor_sync(0xffffffffu, gs3, o);
-          gs4 += __shfl_xor_sync(0xffffffffu, gs4, o);
+    if (!TRAIN) {
+      if (p.grid.on) {  // one row of quadrature sums per CTA, fixed order
+        double* red = reinterpret_cast<double*>(stash);
+        if (role == 0) {
+  #pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gs1 += __shfl_xor_sync(0xffffffffu, gs1, o);
+            gs2 += __shfl_xor_sync(0xffffffffu, gs2, o); gs3 += __shfl_xor_sync(0xffffffffu, gs3, o);
+            gs4 += __shfl_xor_sync(0xffffffffu, gs4, o);
+          }
+          if (lane == 0) { red[grp * 8 + 0] = gs0; red[grp * 8 + 1] = gs1; red[grp * 8 + 2] = gs2; red[grp * 8 + 3] = gs3; red[grp * 8 + 4] = gs4; }
         }
-        if (lane == 0) { red[grp * 8 + 0] = gs0; red[grp * 8 + 1] = gs1; red[grp * 8 + 2] = gs2; red[grp * 8 + 3] = gs3; red[grp * 8 + 4] = gs4; }
+        __syncthreads();
+        if (tid < 5) p.grid.partials[8 * (size_t)blockIdx.x + tid] = (red[tid] + red[8 + tid]) + (red[16 + tid] + red[24 + tid]);
       }
-      __syncthreads();
-      if (tid < 5) p.grid.partials[8 * (size_t)blockIdx.x + tid] = (red[tid] + red[8 + tid]) + (red[16 + tid] + red[24 + tid]);
+      return;
     }
-    return;
-  }
 
-  // ---- fold: every warp writes its accumulators into its own row of floats (the stash is free now), then all
-  //      threads add the rows entry by entry in a fixed order, in double -> one deterministic row per CTA ----
-  {
-    float* myrow = stash + warp * NPART;
-    for (int i = lane; i < NPART; i += 32) myrow[i] = 0.0f;
-    __syncwarp();
-    const int gq = lane >> 2, tq = lane & 3;
-    if (is_mlp) {
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0] + acc.c[1][nt][0];
-        myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1] + acc.c[1][nt][1];
-        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2] + acc.c[1][nt][2];
-        myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3] + acc.c[1][nt][3];
-      }
-      // window index i (0..31) of each vector sum -> entry of the row
-      auto e0 = [](int i) { return i < 16 ? O_B2 + i : O_WO + i - 16; };
-      auto e1 = [](int i) { return i < 16 ? O_W1 + 2 * i : O_W1 + 2 * (i - 16) + 1; };
-      auto e2 = [role](int i) {
-        if (i < 16) return (int)O_B1 + i;
-        if (role != 0) return -1;
-        const int e = i - 16;
-        return e == 0 ? (int)S_RES2 : e == 1 ? (int)S_PSI1 : e == 2 ? (int)S_PSI2 : e == 3 ? (int)S_E
-             : e == 4 ? (int)O_BO : e == 5 ? (int)S_CNT1 : e == 6 ? (int)S_CNT2 : -1;
-      };
-      fold_pair(myrow, acc.s0, lane, e0);
-      fold_pair(myrow, acc.s1, lane, e1);
-      fold_pair(myrow, acc.s2, lane, e2);
-    } else {
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          const int j = mt * 16 + gq, k = nt * 8 + 2 * tq;
-          myrow[O_WE2 + j * NE + k] = acc.c[mt][nt][0];
-          myrow[O_WE2 + j * NE + k + 1] = acc.c[mt][nt][1];
-          myrow[O_WE2 + (j + 8) * NE + k] = acc.c[mt][nt][2];
-          myrow[O_WE2 + (j + 8) * NE + k + 1] = acc.c[mt][nt][3];
+    // ---- fold: every warp writes its accumulators into its own row of floats (the stash is free now), then all
+    //      threads add the rows entry by entry in a fixed order, in double -> one deterministic row per CTA ----
+    {
+      float* myrow = stash + warp * NPART;
+      for (int i = lane; i < NPART; i += 32) myrow[i] = 0.0f;
+      __syncwarp();
+      const int gq = lane >> 2, tq = lane & 3;
+      if (IS_MLP) {
+  #pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0] + acc.c[1][nt][0];
+          myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1] + acc.c[1][nt][1];
+          myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2] + acc.c[1][nt][2];
+          myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3] + acc.c[1][nt][3];
         }
-      fold_pair(myrow, acc.s0, lane, [](int i) { return (int)O_WE + i; });
-      fold_pair(myrow, acc.s1, lane, [](int i) { return (int)O_BE2 + i; });
-      fold_pair(myrow, acc.s2, lane, [](int i) { return (int)O_WE1 + i; });
-      fold_pair(myrow, acc.s3, lane, [](int i) { return (int)O_BE1 + i; });
-      fold_pair(myrow, acc.s4, lane, [](int i) {
-        return i < 10 ? (int)O_WGL + i : i < 20 ? (int)O_BGL + i - 10 : i < 30 ? (int)O_WG + i - 20 : i == 30 ? (int)O_BG : (int)O_BE;
-      });
+        // window index i (0..31) of each vector sum -> entry of the row
+        auto e0 = [](int i) { return i < 16 ? O_B2 + i : O_WO + i - 16; };
+        auto e1 = [](int i) { return i < 16 ? O_W1 + 2 * i : O_W1 + 2 * (i - 16) + 1; };
+        auto e2 = [role](int i) {
+          if (i < 16) return (int)O_B1 + i;
+          if (role != 0) return -1;
+          const int e = i - 16;
+          return e == 0 ? (int)S_RES2 : e == 1 ? (int)S_PSI1 : e == 2 ? (int)S_PSI2 : e == 3 ? (int)S_E
+               : e == 4 ? (int)O_BO : e == 5 ? (int)S_CNT1 : e == 6 ? (int)S_CNT2 : -1;
+        };
+        fold_pair(myrow, acc.s0, lane, e0);
+        fold_pair(myrow, acc.s1, lane, e1);
+        fold_pair(myrow, acc.s2, lane, e2);
+      } else {
+  #pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+  #pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int j = mt * 16 + gq, k = nt * 8 + 2 * tq;
+            myrow[O_WE2 + j * NE + k] = acc.c[mt][nt][0];
+            myrow[O_WE2 + j * NE + k + 1] = acc.c[mt][nt][1];
+            myrow[O_WE2 + (j + 8) * NE + k] = acc.c[mt][nt][2];
+            myrow[O_WE2 + (j + 8) * NE + k + 1] = acc.c[mt][nt][3];
+          }
+        fold_pair(myrow, acc.s0, lane, [](int i) { return (int)O_WE + i; });
+        fold_pair(myrow, acc.s1, lane, [](int i) { return (int)O_BE2 + i; });
+        fold_pair(myrow, acc.s2, lane, [](int i) { return (int)O_WE1 + i; });
+        fold_pair(myrow, acc.s3, lane, [](int i) { return (int)O_BE1 + i; });
+        fold_pair(myrow, acc.s4, lane, [](int i) {
+          return i < 10 ? (int)O_WGL + i : i < 20 ? (int)O_BGL + i - 10 : i < 30 ? (int)O_WG + i - 20 : i == 30 ? (int)O_BG : (int)O_BE;
+        });
+      }
     }
+    __syncthreads();
+    constexpr int nwarps = (NEV + 1) * G;
+    double* row = p.partials + (size_t)blockIdx.x * NPART;
+    for (int i = tid; i < NPART; i += blockDim.x) {
+      double sum = 0.0;
+  #pragma unroll
+      for (int wv = 0; wv < nwarps; wv++) sum += (double)stash[wv * NPART + i];
+      row[i] = sum;
+    }
+    TLK(41);
+  };
+  constexpr bool REBALANCE = TRAIN && NEV == 2;  // 3 warpgroups at 168 registers: 128 * REG_ENET + 256 * REG_MLP = 384 * 168
+  if (is_mlp) {
+    if constexpr (REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REG_MLP));
+    run_role(std::true_type{});
+  } else {
+    if constexpr (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REG_ENET));
+    run_role(std::false_type{});
   }
-  __syncthreads();
-  constexpr int nwarps = (NEV + 1) * G;
-  double* row = p.partials + (size_t)blockIdx.x * NPART;
-  for (int i = tid; i < NPART; i += blockDim.x) {
-    double sum = 0.0;
-#pragma unroll
-    for (int wv = 0; wv < nwarps; wv++) sum += (double)stash[wv * NPART + i];
-    row[i] = sum;
-  }
-  TLK(41);
 }
 
 // =================================================================================================
