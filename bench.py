@@ -223,8 +223,10 @@ def main():
     h = pk.Handle.get(local)
     h.set_engine(args.engine)
     fused = world > 1 and args.allreduce == "fused"
-    if fused:
-        dp.attach_fused(h)
+    if fused and not dp.attach_fused(h, strict=False):
+        fused = False   # all ranks agreed: no peer mapping on this box -> the NCCL all-reduce path (reported in config)
+        if rank == 0:
+            print("bench: fused exchange unavailable, falling back to --allreduce nccl", file=sys.stderr)
 
     theta = torch.from_numpy(load_theta().astype(np.float32)).to(dev)
     host_batches = [synth_batch(n, 1000 * rank + b).pin_memory() for b in range(N_BATCHES)]

@@ -56,18 +56,40 @@ def make_gpu_local_step(variant, x, y, z, R, theta, mask=None, grad_mask=0xFFFF)
     return step
 
 
-def attach_fused(handle, group=None):
+def attach_fused(handle, group=None, strict=True):
     """Connect `handle` (one per rank/GPU) to the other ranks of `group` for the fused exchange and enable it.
 
-    Collective: every rank of the group must call it.  Returns the world size."""
+    Collective: every rank of the group must call it.  The ranks agree on the outcome: if mapping the peers' buffers
+    fails on ANY rank (no CUDA IPC between the processes, no peer access), every rank tears its side down again and the
+    call raises (strict) or returns 0, so that the caller can fall back to ``dp_loss_and_grad`` on all ranks together.
+    Returns the world size on success."""
+    import torch
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    mine = handle.dp_init(rank, world)
+    err = None
+    try:
+        mine = handle.dp_init(rank, world)
+    except Exception as e:  # noqa: BLE001 - reported to all ranks below
+        mine, err = b"\0" * handle.DP_HANDLE_BYTES, e
     allh = [None] * world
     dist.all_gather_object(allh, mine, group=group)
-    handle.dp_connect(allh)
-    dist.barrier(group)   # nobody starts exchanging before every peer has mapped every buffer
-    return world
+    if err is None:
+        try:
+            handle.dp_connect(allh)
+        except Exception as e:  # noqa: BLE001
+            err = e
+    dev = torch.device("cuda", handle.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also the barrier: nobody exchanges before all have mapped
+    if int(ok.item()) == 1:
+        return world
+    try:
+        handle.dp_shutdown()
+    except Exception:  # noqa: BLE001 - nothing was set up on this rank
+        pass
+    if strict:
+        raise RuntimeError("fused data-parallel exchange could not be set up on every rank" + (": %s" % err if err else ""))
+    return 0
 
 
 def detach_fused(handle, group=None):
