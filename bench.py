@@ -356,10 +356,11 @@ def main():
         value = total_points * K / (ms * 1e-3)
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = FLOP_PER_POINT * n / (kern_avg_ms * 1e-3)
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        traffic, ncu_pipes = None, None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")   # numbers of the committed ncu --set full capture of this kernel
+        if os.path.exists(tf) and args.engine == "tcgen05":
+            tj = json.load(open(tf))
+            traffic, ncu_pipes = tj.get("dram_bytes_per_launch"), tj.get("ncu_pipe_utilisation_pct")
         line = {
             "metric": "collocation points/sec per training step (fwd+lap+bwd)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -377,7 +378,8 @@ def main():
                          "peak_source": "measured FFMA rate on this pool's B200 (tools/microbench/pipes.cu); MEASURED_PEAKS.json has no FP32 entry",
                          "flop_per_point": FLOP_PER_POINT, "engine": args.engine,
                          "kernel": "pinn_step_tc_kernel<2,true>" if args.engine == "tcgen05" else "pinn_step_kernel<2,4,true>",
-                         "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic},
+                         "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes},
             "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
                     "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke, "kernel_ms": e2e_kern_ms / max(e2e_kern_n, 1),
                     "last_call_us": {k: round(v, 1) for k, v in e2e_split.items()},
