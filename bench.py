@@ -328,21 +328,25 @@ def main():
     loop = None
     if world == 1 or fused:
         tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6, device=local)
-        tr.run(20)
-        tr.read()
         Kl = max(10, min(K, 300))
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ts = torch.cuda.ExternalStream(tr.h.L.pinn_trainer_stream(tr.t), device=dev)
-        l0.record(ts)
-        tr.run(Kl)
-        l1.record(ts)
-        tr.read()
-        lms = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(lms, op=dist.ReduceOp.MAX)
-        loop = {"value": n * world * Kl / (float(lms.item()) * 1e-3), "unit": "points/s", "steps": Kl,
-                "what": "pinn_trainer: Philox sampler + fused loss/gradient%s + float64 Adam per step, one CUDA-graph replay "
-                        "each, no host sync" % (" + set-size and gradient exchange over NVLink" if world > 1 else "")}
+        res = {}
+        for graph in (False, True):
+            tr.run(20, use_graph=graph)
+            tr.read()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record(ts)
+            tr.run(Kl, use_graph=graph)
+            l1.record(ts)
+            tr.read()
+            lms = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+            res[graph] = n * world * Kl / (float(lms.item()) * 1e-3)
+        loop = {"value": res[False], "unit": "points/s", "steps": Kl, "value_with_cuda_graph_replay": res[True],
+                "what": "pinn_trainer: per step the fused loss/gradient kernel and one kernel with reduction%s + float64 Adam + "
+                        "Philox sampler of the next batch, launched as programmatic dependents, no host sync"
+                        % (" + set-size and gradient exchange over NVLink" if world > 1 else "")}
         tr.close()
 
     # ---- two more reference points for N = 1 (BASELINE configs 2 and 5) ----

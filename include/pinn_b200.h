@@ -208,8 +208,11 @@ int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const do
                    int64_t n, double lr, double beta1, double beta2, double eps, uint32_t grad_mask, int best_mode,
                    int64_t best_after, int history_mean_E, void* stream);
 
-/* Device-resident training loop: sampler -> fused loss/gradient -> Adam, one CUDA-graph replay per step, no host
- * synchronisation until pinn_trainer_read.  Mirrors train() of train.py:21-72 and poc/main.py:359-430. */
+/* Device-resident training loop, no host synchronisation until pinn_trainer_read.  Mirrors train() of train.py:21-72 and
+ * poc/main.py:359-430.  A step is two launches chained as programmatic dependents: the fused loss/gradient kernel, and
+ * one kernel that reduces the per-CTA rows (and exchanges them with the data-parallel peers), applies the float64 Adam
+ * step with the reference loops' bookkeeping, and - in extra blocks - draws the batch of the next step into the
+ * trainer's second batch buffer.  pinn_trainer_run(use_graph = 1) replays captured CUDA graphs of the same launches. */
 typedef struct pinn_train_config {
   int variant;               /* PINN_VARIANT_* */
   int best_mode;             /* 0 train.py, 1 poc (see pinn_adam_step) */

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "pinn_handle.h"
+#include "pinn_train.h"
 
 std::string g_create_err;
 
@@ -324,7 +325,7 @@ int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, con
                       const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
                       const float* theta_inline, const double* weights_inline, uint32_t grad_mask, float bcutoff,
                       double* sums, double* dtheta, float* E_out, cudaStream_t st, const AdamParams* adam,
-                      unsigned long long* adam_ticket) {
+                      unsigned long long* adam_ticket, const SampleParams* presample) {
   std::lock_guard<std::mutex> lk(h->mu);
   StepParams p{};
   int nev = 0;
@@ -354,7 +355,7 @@ int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, con
   int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
   if (rc) return rc;
   CU(h, launch_reduce(h->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
-                      h->dp_on ? h->dp : DpArgs(), st, adam, adam_ticket));
+                      h->dp_on ? h->dp : DpArgs(), st, adam, adam_ticket, presample));
   h->launches++;
   return 0;
 }

@@ -66,12 +66,13 @@ struct DevGuard {
 // The training evaluation behind pinn_loss_fwd_bwd / pinn_loss_fwd_bwd_host / the trainer (pinn_capi.cu).
 // theta / weights: device pointers, or NULL with theta_inline / weights_inline = HOST arrays that travel inside the
 // kernel parameters (tcgen05 engine).  adam (optional): optimizer step fused behind the reduction (the trainer).
-namespace pinn { struct AdamParams; }
+// presample (optional): the trainer's next batch drawn by extra blocks of the reduction kernel.
+namespace pinn { struct AdamParams; struct SampleParams; }
 int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z, const void* R,
                       int in_dtype, const uint8_t* mask, const float* theta, const double* weights, const float* theta_inline,
                       const double* weights_inline, uint32_t grad_mask, float bcutoff, double* sums, double* dtheta,
                       float* E_out, cudaStream_t st, const pinn::AdamParams* adam = nullptr,
-                      unsigned long long* adam_ticket = nullptr);
+                      unsigned long long* adam_ticket = nullptr, const pinn::SampleParams* presample = nullptr);
 
 extern std::string g_create_err;
 

@@ -22,6 +22,7 @@
 //   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
 //     in double precision in a fixed order (deterministic).
 #include "pinn_device.cuh"
+#include "pinn_sample.cuh"
 #include "pinn_train.h"
 
 namespace pinn {
@@ -699,12 +700,25 @@ struct AdamFuse {
   AdamParams a;
   unsigned long long* ticket;  // device, zero between launches
 };
+// The batch of the NEXT step drawn by extra blocks of this launch (blocks DP_BLOCKS .. gridDim.x-1), into the trainer's
+// other batch buffer: the sampler overlaps the reduction / optimizer step instead of standing between two kernels.
+struct SampleFuse {
+  int on;
+  SampleParams s;
+};
+constexpr int PRESAMPLE_BLOCKS = 96;
 __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
                                                               const double* __restrict__ weights, const RedWeights wi,
                                                               uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
                                                               const float* __restrict__ E_out, long long n, const DpArgs dp,
-                                                              const AdamFuse ad) {
+                                                              const AdamFuse ad, const SampleFuse sf) {
+  if (blockIdx.x >= DP_BLOCKS) {
+    // sampler blocks: they touch nothing the step kernel in front reads or writes (other batch buffer), so they do not
+    // wait for it; the reduction blocks below do, which also keeps this grid from completing early
+    if (sf.on) sample_block(sf.s, blockIdx.x - DP_BLOCKS, gridDim.x - DP_BLOCKS);
+    return;
+  }
   __shared__ double sh[RED_SLICES][33];
   __shared__ double tot[32];
   __shared__ double l3[3];
@@ -765,7 +779,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
     __syncthreads();
     if (threadIdx.x == 0) {  // the last block of the launch closes the exchange (the next launch is stream-ordered behind it)
       __threadfence();
-      if (atomicAdd(&ctl[1], 1ull) == (unsigned long long)gridDim.x - 1) {
+      if (atomicAdd(&ctl[1], 1ull) == (unsigned long long)DP_BLOCKS - 1) {
         ctl[1] = 0ull;
         st_release_sys(&ctl[0], step64);
       }
@@ -850,7 +864,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    flag_s = atomicAdd(ad.ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+    flag_s = atomicAdd(ad.ticket, 1ull) == (unsigned long long)DP_BLOCKS - 1;
     if (flag_s) {  // every block has updated its parameters and read the step / best loss; the loss sums are visible
       __threadfence();
       const double sv[8] = {ld_acquire_gpu(&sums[0]), ld_acquire_gpu(&sums[1]), ld_acquire_gpu(&sums[2]), ld_acquire_gpu(&sums[3]),
@@ -907,13 +921,16 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
-                          cudaStream_t st, const AdamParams* adam, unsigned long long* adam_ticket) {
+                          cudaStream_t st, const AdamParams* adam, unsigned long long* adam_ticket,
+                          const SampleParams* presample) {
   AdamFuse ad{};
   if (adam) { ad.on = 1; ad.a = *adam; ad.ticket = adam_ticket; }
+  SampleFuse sf{};
+  if (presample) { sf.on = 1; sf.s = *presample; }
   RedWeights wi{};
   if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
-  return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS), dim3(RED_SLICES * 32), 0, st, partials, nrows, weights, wi, grad_mask, dtheta,
-                    sums, E_out, n, dp, ad);
+  return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS + (presample ? PRESAMPLE_BLOCKS : 0)), dim3(RED_SLICES * 32), 0, st,
+                    partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp, ad, sf);
 }
 
 }  // namespace pinn

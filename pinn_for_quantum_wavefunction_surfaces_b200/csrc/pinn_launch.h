@@ -89,9 +89,12 @@ struct DpArgs {
 };
 // weights: device pointer, or NULL with weights_inline (host, 3 double) carried in the kernel parameters
 // adam (optional): the optimizer step of the device-resident trainer fused behind the reduction (pinn_train.h)
+// presample (optional): extra blocks of the same launch draw the trainer's next batch (pinn_sample.cuh)
 struct AdamParams;
+struct SampleParams;
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
-                          cudaStream_t st, const AdamParams* adam = nullptr, unsigned long long* adam_ticket = nullptr);
+                          cudaStream_t st, const AdamParams* adam = nullptr, unsigned long long* adam_ticket = nullptr,
+                          const SampleParams* presample = nullptr);
 
 }  // namespace pinn

@@ -15,32 +15,50 @@ struct pinn_trainer {
   pinn_handle* h = nullptr;
   pinn_train_config cfg{};
   cudaStream_t st = nullptr;
-  float *x = nullptr, *y = nullptr, *z = nullptr, *R = nullptr, *E = nullptr, *theta32 = nullptr;
-  uint8_t* mask = nullptr;
-  unsigned long long *counts = nullptr, *batch = nullptr, *step = nullptr;
+  // two batch buffers: the step works on buffer `cur` while the sampler blocks riding in its reduction kernel draw the
+  // next batch into the other one
+  float *x[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr}, *z[2] = {nullptr, nullptr}, *R[2] = {nullptr, nullptr};
+  uint8_t* mask[2] = {nullptr, nullptr};
+  double* weights[2] = {nullptr, nullptr};
+  unsigned long long* counts[2] = {nullptr, nullptr};  // per buffer {|set1|, |set2|, sampler ticket, -}
+  int cur = 0;
+  bool next_ready = false;  // buffer cur^1 holds the batch of the next step
+  float *E = nullptr, *theta32 = nullptr;
+  unsigned long long *batch = nullptr, *step = nullptr, *adam_ticket = nullptr;
   long long* best_step = nullptr;
-  double *weights = nullptr, *theta = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr, *sums = nullptr;
+  double *theta = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr, *sums = nullptr;
   double *best_loss = nullptr, *best_theta = nullptr, *hist = nullptr;
-  cudaGraphExec_t g_resample = nullptr, g_keep = nullptr;
+  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [cur][draw the next batch too]
+  bool warmed = false;  // one plain step has run: one-time kernel attributes are set outside any capture
   int64_t steps_issued = 0;
   bool have_batch = false;
 };
 
-static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
+static SampleParams sampler_params(pinn_trainer* t, int buf) {
   pinn_handle* h = t->h;
   const pinn_train_config& c = t->cfg;
-  if (resample) {
-    SampleParams s{};
-    s.n = c.n; s.seed = c.seed; s.batch_counter = t->batch;
-    s.xL = c.xL; s.xR = c.xR; s.yL = c.yL; s.yR = c.yR; s.zL = c.zL; s.zR = c.zR; s.RL = c.RL; s.RR = c.RR;
-    s.cutoff = c.cutoff; s.bcutoff = c.bcutoff;
-    s.x = t->x; s.y = t->y; s.z = t->z; s.R = t->R; s.mask = t->mask; s.counts = t->counts;
-    // data-parallel: rank r draws points [r n, (r+1) n) of the global batch of world*n points, so the union over the
-    // ranks is exactly the batch a single GPU would draw for n_global = world*n
-    const bool dp_run = h->dp_on && h->dp.world > 1;
-    s.index_offset = dp_run ? (long long)h->dp.rank * c.n : 0;
-    s.weights = t->weights; s.ticket = t->counts + 2; s.reset_counts = 1;
-    if (dp_run) s.dp = h->dp;
+  SampleParams s{};
+  s.n = c.n; s.seed = c.seed; s.batch_counter = t->batch;
+  s.xL = c.xL; s.xR = c.xR; s.yL = c.yL; s.yR = c.yR; s.zL = c.zL; s.zR = c.zR; s.RL = c.RL; s.RR = c.RR;
+  s.cutoff = c.cutoff; s.bcutoff = c.bcutoff;
+  s.x = t->x[buf]; s.y = t->y[buf]; s.z = t->z[buf]; s.R = t->R[buf]; s.mask = t->mask[buf]; s.counts = t->counts[buf];
+  // data-parallel: rank r draws points [r n, (r+1) n) of the global batch of world*n points, so the union over the
+  // ranks is exactly the batch a single GPU would draw for n_global = world*n
+  const bool dp_run = h->dp_on && h->dp.world > 1;
+  s.index_offset = dp_run ? (long long)h->dp.rank * c.n : 0;
+  s.weights = t->weights[buf]; s.ticket = t->counts[buf] + 2; s.reset_counts = 1;
+  if (dp_run) s.dp = h->dp;
+  return s;
+}
+
+// One optimizer step on buffer t->cur.  sample_now: draw its batch first with the stand-alone sampler kernel (the first
+// resampling step of a run); presample_next: the reduction kernel also draws the batch of the NEXT step into the other buffer.
+static int trainer_enqueue(pinn_trainer* t, bool sample_now, bool presample_next, cudaStream_t st) {
+  pinn_handle* h = t->h;
+  const pinn_train_config& c = t->cfg;
+  const int b = t->cur;
+  if (sample_now) {
+    const SampleParams s = sampler_params(t, b);
     CU(h, launch_sample(s, false, st));
     h->launches += 1;
   }
@@ -51,19 +69,22 @@ static int trainer_enqueue(pinn_trainer* t, bool resample, cudaStream_t st) {
   a.n = c.n * ((h->dp_on && h->dp.world > 1) ? h->dp.world : 1);  // mean E of the history is over the global batch
   a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.eps; a.best_after = (double)c.best_after;
   a.grad_mask = c.grad_mask; a.best_mode = c.best_mode; a.hist_mean_E = c.history_mean_E;
-  // the optimizer step rides in the reduction kernel: two launches per step (three with the sampler)
-  int rc = loss_fwd_bwd_impl(h, c.variant, c.n, t->x, t->y, t->z, t->R, PINN_F32, t->mask, t->theta32, t->weights, nullptr,
-                             nullptr, c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, st, &a, t->counts + 3);
+  SampleParams next{};
+  if (presample_next) next = sampler_params(t, b ^ 1);
+  // the optimizer step (and the next batch) ride in the reduction kernel: two launches per step
+  int rc = loss_fwd_bwd_impl(h, c.variant, c.n, t->x[b], t->y[b], t->z[b], t->R[b], PINN_F32, t->mask[b], t->theta32,
+                             t->weights[b], nullptr, nullptr, c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, st, &a,
+                             t->adam_ticket, presample_next ? &next : nullptr);
   if (rc) return rc;
   return 0;
 }
 
-static int trainer_capture(pinn_trainer* t, bool resample, cudaGraphExec_t* out) {
+static int trainer_capture(pinn_trainer* t, bool presample_next, cudaGraphExec_t* out) {
   pinn_handle* h = t->h;
   cudaGraph_t g = nullptr;
   CU(h, cudaStreamBeginCapture(t->st, cudaStreamCaptureModeThreadLocal));
   const int64_t launches_before = h->launches;
-  int rc = trainer_enqueue(t, resample, t->st);
+  int rc = trainer_enqueue(t, false, presample_next, t->st);
   h->launches = launches_before;  // capture does not launch; replays are counted in pinn_trainer_run
   cudaError_t e = cudaStreamEndCapture(t->st, &g);
   if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -181,11 +202,16 @@ int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const doub
   *out = nullptr;
   const size_t n = (size_t)cfg->n;
   TRAINER_CU(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
-  TRAINER_CU(cudaMalloc(&t->x, n * 4)); TRAINER_CU(cudaMalloc(&t->y, n * 4)); TRAINER_CU(cudaMalloc(&t->z, n * 4));
-  TRAINER_CU(cudaMalloc(&t->R, n * 4)); TRAINER_CU(cudaMalloc(&t->E, n * 4)); TRAINER_CU(cudaMalloc(&t->mask, n));
+  for (int b = 0; b < 2; b++) {
+    TRAINER_CU(cudaMalloc(&t->x[b], n * 4)); TRAINER_CU(cudaMalloc(&t->y[b], n * 4)); TRAINER_CU(cudaMalloc(&t->z[b], n * 4));
+    TRAINER_CU(cudaMalloc(&t->R[b], n * 4)); TRAINER_CU(cudaMalloc(&t->mask[b], n));
+    TRAINER_CU(cudaMalloc(&t->weights[b], 4 * 8));
+    TRAINER_CU(cudaMalloc(&t->counts[b], 32)); TRAINER_CU(cudaMemset(t->counts[b], 0, 32));
+  }
+  TRAINER_CU(cudaMalloc(&t->E, n * 4));
   TRAINER_CU(cudaMalloc(&t->theta32, NPART * 4));
-  TRAINER_CU(cudaMalloc(&t->counts, 32)); TRAINER_CU(cudaMemset(t->counts, 0, 32)); TRAINER_CU(cudaMalloc(&t->batch, 8)); TRAINER_CU(cudaMalloc(&t->step, 8)); TRAINER_CU(cudaMalloc(&t->best_step, 8));
-  TRAINER_CU(cudaMalloc(&t->weights, 4 * 8));
+  TRAINER_CU(cudaMalloc(&t->batch, 8)); TRAINER_CU(cudaMalloc(&t->step, 8)); TRAINER_CU(cudaMalloc(&t->best_step, 8));
+  TRAINER_CU(cudaMalloc(&t->adam_ticket, 8)); TRAINER_CU(cudaMemset(t->adam_ticket, 0, 8));
   TRAINER_CU(cudaMalloc(&t->theta, NPART * 8)); TRAINER_CU(cudaMalloc(&t->m, NPART * 8)); TRAINER_CU(cudaMalloc(&t->v, NPART * 8));
   TRAINER_CU(cudaMalloc(&t->grad, NPART * 8)); TRAINER_CU(cudaMalloc(&t->sums, 8 * 8));
   TRAINER_CU(cudaMalloc(&t->best_loss, 8)); TRAINER_CU(cudaMalloc(&t->best_theta, NPART * 8));
@@ -212,10 +238,14 @@ int pinn_trainer_destroy(pinn_trainer* t) {
   if (!t) return 0;
   DevGuard dev_guard(t->h->device);
   if (t->st) cudaStreamSynchronize(t->st);
-  if (t->g_resample) cudaGraphExecDestroy(t->g_resample);
-  if (t->g_keep) cudaGraphExecDestroy(t->g_keep);
-  cudaFree(t->x); cudaFree(t->y); cudaFree(t->z); cudaFree(t->R); cudaFree(t->E); cudaFree(t->mask); cudaFree(t->theta32);
-  cudaFree(t->counts); cudaFree(t->batch); cudaFree(t->step); cudaFree(t->best_step); cudaFree(t->weights);
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++)
+      if (t->graph[a][b]) cudaGraphExecDestroy(t->graph[a][b]);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(t->x[b]); cudaFree(t->y[b]); cudaFree(t->z[b]); cudaFree(t->R[b]); cudaFree(t->mask[b]);
+    cudaFree(t->weights[b]); cudaFree(t->counts[b]);
+  }
+  cudaFree(t->E); cudaFree(t->theta32); cudaFree(t->batch); cudaFree(t->step); cudaFree(t->best_step); cudaFree(t->adam_ticket);
   cudaFree(t->theta); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad); cudaFree(t->sums);
   cudaFree(t->best_loss); cudaFree(t->best_theta); cudaFree(t->hist);
   if (t->st) cudaStreamDestroy(t->st);
@@ -251,51 +281,56 @@ int pinn_trainer_set_batch(pinn_trainer* t, const float* x, const float* y, cons
   if (!x || !y || !z || !R || !mask || !weights_host) return fail(h, PINN_EINVAL, "pinn_trainer_set_batch: NULL pointer argument");
   DevGuard dev_guard(h->device);
   const size_t n = (size_t)t->cfg.n;
-  CU(h, cudaMemcpyAsync(t->x, x, n * 4, cudaMemcpyDefault, t->st));
-  CU(h, cudaMemcpyAsync(t->y, y, n * 4, cudaMemcpyDefault, t->st));
-  CU(h, cudaMemcpyAsync(t->z, z, n * 4, cudaMemcpyDefault, t->st));
-  CU(h, cudaMemcpyAsync(t->R, R, n * 4, cudaMemcpyDefault, t->st));
-  CU(h, cudaMemcpyAsync(t->mask, mask, n, cudaMemcpyDefault, t->st));
-  CU(h, cudaMemcpyAsync(t->weights, weights_host, 3 * 8, cudaMemcpyDefault, t->st));
+  const int b = t->cur;
+  CU(h, cudaMemcpyAsync(t->x[b], x, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->y[b], y, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->z[b], z, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->R[b], R, n * 4, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->mask[b], mask, n, cudaMemcpyDefault, t->st));
+  CU(h, cudaMemcpyAsync(t->weights[b], weights_host, 3 * 8, cudaMemcpyDefault, t->st));
   CU(h, cudaStreamSynchronize(t->st));
   t->have_batch = true;
   return 0;
 }
 
 // Enqueue `steps` optimizer steps.  Step tt resamples iff tt % sc_sampling == 0 and tt < freeze_after (poc/main.py:396;
-// train.py:25) - or never, when resample == 0 (the batch of pinn_trainer_set_batch is kept).  use_graph: replay two
-// captured CUDA graphs (sample+loss+Adam / loss+Adam) instead of launching the 7 kernels of a step one by one.
+// train.py:25) - or never, when resample == 0 (the batch of pinn_trainer_set_batch is kept).  The batch of a resampling
+// step is drawn by sampler blocks inside the reduction kernel of the step before it (into the other batch buffer) when
+// that step belongs to the same call; the first resampling step of a call uses the stand-alone sampler kernel.  The
+// sequence of batches is the same either way.  use_graph: steps without a stand-alone sampler replay one of four captured
+// CUDA graphs (which buffer x whether the next batch is drawn) instead of launching their two kernels.
 int pinn_trainer_run(pinn_trainer* t, int64_t steps, int resample, int use_graph) {
   if (!t) return PINN_EINVAL;
   pinn_handle* h = t->h;
   if (steps < 0) return fail(h, PINN_EINVAL, "pinn_trainer_run: steps must be >= 0");
   if (!resample && !t->have_batch) return fail(h, PINN_EINVAL, "pinn_trainer_run: no batch yet (resample = 0 needs pinn_trainer_set_batch or an earlier sampled step)");
   DevGuard dev_guard(h->device);
-  if (use_graph && !t->g_keep) {
-    // one plain step first: one-time kernel attributes are set outside the capture
-    if (steps == 0) return 0;
-    const bool rs = resample && (t->steps_issued % t->cfg.sc_sampling == 0) && (t->steps_issued < t->cfg.freeze_after);
-    int rc = trainer_enqueue(t, rs, t->st);
-    if (rc) return rc;
-    if (rs) t->have_batch = true;
-    t->steps_issued++;
-    steps--;
-    CU(h, cudaStreamSynchronize(t->st));
-    rc = trainer_capture(t, true, &t->g_resample);
-    if (rc) return rc;
-    rc = trainer_capture(t, false, &t->g_keep);
-    if (rc) return rc;
-  }
+  auto resamples = [&](int64_t tt) { return resample && (tt % t->cfg.sc_sampling == 0) && (tt < t->cfg.freeze_after); };
   for (int64_t k = 0; k < steps; k++) {
     const int64_t tt = t->steps_issued;
-    const bool rs = resample && (tt % t->cfg.sc_sampling == 0) && (tt < t->cfg.freeze_after);
-    if (use_graph) {
-      CU(h, cudaGraphLaunch(rs ? t->g_resample : t->g_keep, t->st));
-      h->launches += rs ? 3 : 2;
-    } else {
-      int rc = trainer_enqueue(t, rs, t->st);
-      if (rc) return rc;
+    const bool rs = resamples(tt);
+    bool sample_now = false;
+    if (rs) {
+      if (t->next_ready) { t->cur ^= 1; t->next_ready = false; }  // drawn while the previous step was reduced
+      else sample_now = true;
     }
+    const bool presample_next = (k + 1 < steps) && resamples(tt + 1);
+    if (use_graph && t->warmed && !sample_now) {
+      cudaGraphExec_t& g = t->graph[t->cur][presample_next ? 1 : 0];
+      if (!g) {
+        int rc = trainer_capture(t, presample_next, &g);
+        if (rc) return rc;
+      }
+      CU(h, cudaGraphLaunch(g, t->st));
+      h->launches += 2;
+    } else {
+      // plain launches: the first step ever (one-time kernel attributes are set outside any capture) and steps that
+      // start with the stand-alone sampler
+      int rc = trainer_enqueue(t, sample_now, presample_next, t->st);
+      if (rc) return rc;
+      t->warmed = true;
+    }
+    if (presample_next) t->next_ready = true;
     if (rs) t->have_batch = true;
     t->steps_issued++;
   }
@@ -333,11 +368,12 @@ int pinn_trainer_read(pinn_trainer* t, double* theta, double* m, double* v, doub
 // Device pointers of the current batch (x, y, z, R float32; mask bytes), e.g. to inspect what the sampler drew.
 int pinn_trainer_batch(pinn_trainer* t, float** x, float** y, float** z, float** R, uint8_t** mask) {
   if (!t) return PINN_EINVAL;
-  if (x) *x = t->x;
-  if (y) *y = t->y;
-  if (z) *z = t->z;
-  if (R) *R = t->R;
-  if (mask) *mask = t->mask;
+  const int b = t->cur;  // the batch of the last enqueued step
+  if (x) *x = t->x[b];
+  if (y) *y = t->y[b];
+  if (z) *z = t->z[b];
+  if (R) *R = t->R[b];
+  if (mask) *mask = t->mask[b];
   return 0;
 }
 
