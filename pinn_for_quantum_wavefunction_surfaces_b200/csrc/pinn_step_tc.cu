@@ -926,9 +926,9 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     // ---- fold: every warp writes its accumulators into its own row of floats (the stash is free now), then all
     //      threads add the rows entry by entry in a fixed order, in double -> one deterministic row per CTA ----
     {
+      // (no zero fill: every MLP warp writes all base-MLP entries, role 0 also bo and the loss sums, every E-net warp
+      // all E-net and gate entries; the final sum below only reads the rows of the warps that own an entry)
       float* myrow = stash + warp * NPART;
-      for (int i = lane; i < NPART; i += 32) myrow[i] = 0.0f;
-      __syncwarp();
       const int gq = lane >> 2, tq = lane & 3;
       if (IS_MLP) {
   #pragma unroll
@@ -975,9 +975,14 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     constexpr int nwarps = (NEV + 1) * G;
     double* row = p.partials + (size_t)blockIdx.x * NPART;
     for (int i = tid; i < NPART; i += blockDim.x) {
+      // owners of entry i: base-MLP weights <- all MLP warps; bo and the loss sums <- role 0; E-net and gate <- E-net warps
+      int w0, w1;
+      if (i < O_BO) { w0 = 0; w1 = NEV * G; }
+      else if (i == O_BO || (i >= S_RES2 && i <= S_CNT2)) { w0 = 0; w1 = G; }
+      else if (i < NTHETA) { w0 = NEV * G; w1 = nwarps; }
+      else { w0 = 0; w1 = 0; }  // padding
       double sum = 0.0;
-  #pragma unroll
-      for (int wv = 0; wv < nwarps; wv++) sum += (double)stash[wv * NPART + i];
+      for (int wv = w0; wv < w1; wv++) sum += (double)stash[wv * NPART + i];
       row[i] = sum;
     }
     TLK(41);
