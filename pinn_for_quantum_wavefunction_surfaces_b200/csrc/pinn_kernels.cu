@@ -1,4 +1,7 @@
-// Fused PINN residual-and-gradient kernels for B200 (sm_100a).
+// Fused PINN residual-and-gradient kernels for B200 (sm_100a): the FFMA engine of the step kernel (the first correct
+// path, kept behind pinn_set_engine for A/B measurement against pinn_step_tc.cu) and the small kernels both engines
+// share - set counting, and the reduction of the per-CTA rows, which is also the data-parallel exchange, the optimizer
+// step and the sampler of the device-resident trainer.
 //
 // What is computed (closed form of the reference's autograd path, oracle/closed_form.py):
 //   psi, lap psi, residual, loss sums and dLtot/dtheta of the parametric H2+ model
@@ -17,8 +20,8 @@
 //     have K = points and are dense: they run on the tensor cores (mma.sync m16n8k8
 //     TF32 with the 3xTF32 split, fp32-accurate), operands staged per warp in shared memory,
 //     accumulators persistent in registers over all tiles of the launch.
-//   * bias/vector gradients and the loss sums are reduced over the 32 points of a tile with a
-//     transposing shuffle butterfly (32 values -> one per lane).
+//   * bias/vector gradients and the loss sums are reduced over the 32 points of a tile by column sums over
+//     the swizzled shared-memory stash (colsum).
 //   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
 //     in double precision in a fixed order (deterministic).
 #include "pinn_device.cuh"

@@ -12,16 +12,21 @@
 //     E-net + gate); the 4 warps of a role form the 128 rows of an M=128 tcgen05.mma.
 //   * every thread writes its row of the A operand (activations, split x = hi + lo with hi = the 19 bits
 //     the tensor core reads) straight from registers into TENSOR MEMORY with tcgen05.st; the B operands
-//     (weights, split the same way, canonical K-major layout) sit in shared memory, staged once per CTA
-//     by a TMA bulk copy; D accumulates in TMEM and comes back with tcgen05.ld.  3xTF32
-//     (lo*hi + hi*lo + hi*hi) keeps fp32 accuracy (tools/microbench/umma_ts.cu: 4e-7 relative).
+//     (weights, split the same way, canonical K-major layout) sit in shared memory, built once per CTA:
+//     theta arrives by one TMA bulk copy (or inside the kernel parameters, INLINE) and all threads turn it
+//     into the operand images (build_weight_image); D accumulates in TMEM and comes back with tcgen05.ld.
+//     3xTF32 (lo*hi + hi*lo + hi*hi) keeps fp32 accuracy (tools/microbench/umma_ts.cu: 4e-7 relative).
 //   * the forward uses the linearity of the Taylor channels in the layer-1 quantities: with A = {s, s', s''}
-//     (3 x 16 columns instead of 4 x 16) and the pre-multiplied operand images BS/BSP/BSPP of
-//     prep_weights_kernel the 4-channel product needs 18 instead of 24 MMAs.
+//     (3 x 16 columns instead of 4 x 16) and the pre-multiplied operand images BS/BSP/BSPP the 4-channel
+//     product needs 18 instead of 24 MMAs.
 //   * an M=128, K=8 TF32 MMA costs ~47 cycles for any N <= 64 (measured), so the tensor pipe is busy
 //     ~40 cycles per point and overlaps the element-wise work of the other roles; the weight-gradient
 //     contractions (K = points) stay on mma.sync, reading the shared-memory stash, and are issued while
 //     the reverse-sweep MMAs are in flight.
+//   * coordinates travel global -> shared with cp.async one super-tile ahead (page-locked host memory
+//     works as a source); the kernel is launched as a programmatic dependent of the kernel in front of it;
+//     the code after the common set-up exists once per kind of role (MLP / E-net) and, in the poc training
+//     kernel, starts with setmaxnreg (the E-net warpgroup lends registers to the two MLP warpgroups).
 #include <cstring>
 #include <type_traits>
 
