@@ -15,6 +15,12 @@ constexpr int EVAL_STASH = 2 * 32 * ROWH;  // floats: Hs + Gs
 constexpr int ENET_STASH = 2 * 32 * ROWE;  // floats: E1s + Vs
 
 __device__ __forceinline__ int swz(int row) { return (row & 3) << 3; }
+// Swizzle of the tcgen05 engine's stash (pinn_step_tc.cu): the 16-byte chunk index of a row is XOR-ed with
+// s(row) = ((row & 3) << 1) | ((row >> 2) & 1).  Eight consecutive rows get eight different values, so the 128-bit
+// accesses of a row by its own lane (quarter-warp = 8 lanes per phase) are conflict-free, and rows r, r+1, r+2, r+3 differ
+// in the upper two bits, which keeps the scalar mma.sync fragment loads (8 columns x 4 rows per instruction)
+// conflict-free as with swz().  Returned in floats (multiple of 4).
+__host__ __device__ constexpr int swz_tc(int row) { return ((((row & 3) << 1) | ((row >> 2) & 1)) << 2); }
 
 // ---------------------------------------------------------------------------------------------
 // small PTX helpers
@@ -113,17 +119,11 @@ __device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col
 template <int ROW>
 __device__ __forceinline__ float2 colsum2(const float* __restrict__ base, int col2, int half) {
   const float* b = base + half * 16 * ROW;
-  const float2* p0 = reinterpret_cast<const float2*>(b + col2);
-  const float2* p1 = reinterpret_cast<const float2*>(b + ROW + (col2 ^ 8));
-  const float2* p2 = reinterpret_cast<const float2*>(b + 2 * ROW + (col2 ^ 16));
-  const float2* p3 = reinterpret_cast<const float2*>(b + 3 * ROW + (col2 ^ 24));
   float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
 #pragma unroll
-  for (int p = 0; p < 16; p += 4) {
-    s0 = __fadd2_rn(s0, p0[p * (ROW / 2)]);
-    s1 = __fadd2_rn(s1, p1[p * (ROW / 2)]);
-    s0 = __fadd2_rn(s0, p2[p * (ROW / 2)]);
-    s1 = __fadd2_rn(s1, p3[p * (ROW / 2)]);
+  for (int p = 0; p < 16; p += 2) {  // swz_tc(16 half + p) = swz_tc(p): compile-time patterns, [pointer + immediate] loads
+    s0 = __fadd2_rn(s0, *reinterpret_cast<const float2*>(b + p * ROW + (col2 ^ swz_tc(p))));
+    s1 = __fadd2_rn(s1, *reinterpret_cast<const float2*>(b + (p + 1) * ROW + (col2 ^ swz_tc(p + 1))));
   }
   return __fadd2_rn(s0, s1);
 }
@@ -132,22 +132,16 @@ template <int ROW>
 __device__ __forceinline__ void colsum2_w(const float* __restrict__ base, int col2, int half, float wgt, float2& plain,
                                           float2& weighted) {
   const float* b = base + half * 16 * ROW;
-  const float2* p0 = reinterpret_cast<const float2*>(b + col2);
-  const float2* p1 = reinterpret_cast<const float2*>(b + ROW + (col2 ^ 8));
-  const float2* p2 = reinterpret_cast<const float2*>(b + 2 * ROW + (col2 ^ 16));
-  const float2* p3 = reinterpret_cast<const float2*>(b + 3 * ROW + (col2 ^ 24));
   float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, t0 = s0, t1 = s0;
   const int r0 = half * 16;
 #pragma unroll
-  for (int p = 0; p < 16; p += 4) {
-    const float2 v0 = p0[p * (ROW / 2)], v1 = p1[p * (ROW / 2)], v2 = p2[p * (ROW / 2)], v3 = p3[p * (ROW / 2)];
-    const float w0 = __shfl_sync(0xffffffffu, wgt, r0 + p + 0), w1 = __shfl_sync(0xffffffffu, wgt, r0 + p + 1);
-    const float w2 = __shfl_sync(0xffffffffu, wgt, r0 + p + 2), w3 = __shfl_sync(0xffffffffu, wgt, r0 + p + 3);
-    s0 = __fadd2_rn(s0, v0); s1 = __fadd2_rn(s1, v1); s0 = __fadd2_rn(s0, v2); s1 = __fadd2_rn(s1, v3);
+  for (int p = 0; p < 16; p += 2) {
+    const float2 v0 = *reinterpret_cast<const float2*>(b + p * ROW + (col2 ^ swz_tc(p)));
+    const float2 v1 = *reinterpret_cast<const float2*>(b + (p + 1) * ROW + (col2 ^ swz_tc(p + 1)));
+    const float w0 = __shfl_sync(0xffffffffu, wgt, r0 + p), w1 = __shfl_sync(0xffffffffu, wgt, r0 + p + 1);
+    s0 = __fadd2_rn(s0, v0); s1 = __fadd2_rn(s1, v1);
     t0 = __ffma2_rn(v0, make_float2(w0, w0), t0);
     t1 = __ffma2_rn(v1, make_float2(w1, w1), t1);
-    t0 = __ffma2_rn(v2, make_float2(w2, w2), t0);
-    t1 = __ffma2_rn(v3, make_float2(w3, w3), t1);
   }
   plain = __fadd2_rn(s0, s1);
   weighted = __fadd2_rn(t0, t1);

@@ -265,7 +265,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
                                                 float al11, float al12, float al22, float lamN, float lamD,
                                                 float* __restrict__ Hs, float* __restrict__ Gs, int lane,
                                                 const float (&extra)[8], TcMlpAcc& acc) {
-  const int sx = swz(lane);
+  const int sx = swz_tc(lane);
   float* Hrow = Hs + lane * ROWH;
   float* Grow = Gs + lane * ROWH;
   float dwo[NH];
@@ -323,7 +323,8 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
 
   // ---- while the tensor core runs: dW2[j][k] += sum_{p,c} G[p][c][j] * H[p][c][k] (mma.sync, 3xTF32) ----
   {
-    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+    // rows po*8 + t and po*8 + t + 4: swz_tc = t << 3 and (t << 3) | 4
+    const int g = lane >> 2, t = lane & 3, tx = t << 3, ty = tx | 4;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ch++) {
 #pragma unroll
@@ -333,19 +334,20 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
         const float* Ha = Hs + (po * 8 + t) * ROWH;
         const float* Hb = Ha + 4 * ROWH;
         const int ca = (ch * NH + g) ^ tx, cbb = (ch * NH + g + 8) ^ tx;
+        const int da = (ch * NH + g) ^ ty, dbb = (ch * NH + g + 8) ^ ty;
         uint32_t ah[4], al[4];
         split_tf32(Ga[ca], ah[0], al[0]);
         split_tf32(Ga[cbb], ah[1], al[1]);
-        split_tf32(Gb[ca], ah[2], al[2]);
-        split_tf32(Gb[cbb], ah[3], al[3]);
+        split_tf32(Gb[da], ah[2], al[2]);
+        split_tf32(Gb[dbb], ah[3], al[3]);
         uint32_t bh0, bl0, bh1, bl1;
         split_tf32(Ha[ca], bh0, bl0);
-        split_tf32(Hb[ca], bh1, bl1);
+        split_tf32(Hb[da], bh1, bl1);
         // even / odd k-steps accumulate into separate fragments: four independent HMMA chains instead of two (the
         // phase is bound by the accumulate latency of the legacy tensor path, not by its throughput)
         mma_3xtf32(acc.c[po & 1][0], ah, al, bh0, bh1, bl0, bl1);
         split_tf32(Ha[cbb], bh0, bl0);
-        split_tf32(Hb[cbb], bh1, bl1);
+        split_tf32(Hb[dbb], bh1, bl1);
         mma_3xtf32(acc.c[po & 1][1], ah, al, bh0, bh1, bl0, bl1);
       }
     }
@@ -412,7 +414,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
 
 // loss sums only (fine-tune mode: no base-MLP reverse sweep); role 0
 __device__ __forceinline__ void tc_mlp_extras_only(float* __restrict__ Hs, int lane, const float (&extra)[8], TcMlpAcc& acc) {
-  const int sx = swz(lane);
+  const int sx = swz_tc(lane);
   float* Hrow = Hs + lane * ROWH;
   __syncwarp();
   ST4(&Hrow[0 ^ sx], extra[0], extra[1], extra[2], extra[3]);
@@ -491,7 +493,7 @@ __device__ __forceinline__ float tc_gate_forward(const Wts& w, float R) {
 
 __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R, float Ebar, float gbar, bool gate_grads,
                                                  float* __restrict__ E1s, float* __restrict__ Vs, int lane, TcEnetAcc& acc) {
-  const int sx = swz(lane);
+  const int sx = swz_tc(lane);
   float* E1row = E1s + lane * ROWE;
   float* Vrow = Vs + lane * ROWE;
   const uint32_t t0 = c.tlane + TC_E_BASE;
@@ -532,7 +534,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   __syncwarp();
   // ---- while the tensor core runs: dWE2[j][k] += sum_p V[p][j] * E1[p][k] (mma.sync, 3xTF32) ----
   {
-    const int g = lane >> 2, t = lane & 3, tx = t << 3;
+    const int g = lane >> 2, t = lane & 3, tx = t << 3, ty = tx | 4;  // swz_tc of rows ks*8 + t and ks*8 + t + 4
 #pragma unroll 1
     for (int ks = 0; ks < 4; ks++) {
       const float* Va = Vs + (ks * 8 + t) * ROWE;
@@ -544,14 +546,14 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
       for (int mt = 0; mt < 2; mt++) {
         split_tf32(Va[(mt * 16 + g) ^ tx], ah[mt][0], al[mt][0]);
         split_tf32(Va[(mt * 16 + g + 8) ^ tx], ah[mt][1], al[mt][1]);
-        split_tf32(Vb[(mt * 16 + g) ^ tx], ah[mt][2], al[mt][2]);
-        split_tf32(Vb[(mt * 16 + g + 8) ^ tx], ah[mt][3], al[mt][3]);
+        split_tf32(Vb[(mt * 16 + g) ^ ty], ah[mt][2], al[mt][2]);
+        split_tf32(Vb[(mt * 16 + g + 8) ^ ty], ah[mt][3], al[mt][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
         uint32_t bh0, bl0, bh1, bl1;
         split_tf32(Ea[(nt * 8 + g) ^ tx], bh0, bl0);
-        split_tf32(Eb[(nt * 8 + g) ^ tx], bh1, bl1);
+        split_tf32(Eb[(nt * 8 + g) ^ ty], bh1, bl1);
         mma_3xtf32(acc.c[0][nt], ah[0], al[0], bh0, bh1, bl0, bl1);
         mma_3xtf32(acc.c[1][nt], ah[1], al[1], bh0, bh1, bl0, bl1);
       }
@@ -654,7 +656,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role/group branches and MMA operands
   const int role = warp >> 2, grp = warp & 3;
   const bool is_mlp = role < NEV;
-  const int sx = swz(lane);
+  const int sx = swz_tc(lane);
   TLK(0);
 
   // ---- one-time setup: TMEM allocation (warp 0), mbarriers, weight image by TMA bulk copy ----
