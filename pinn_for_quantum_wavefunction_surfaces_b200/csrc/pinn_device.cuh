@@ -113,6 +113,14 @@ __device__ __forceinline__ void colsum_w(const float* __restrict__ base, int col
   weighted = t0 + t1;
 }
 
+// packed float32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): one instruction for two independent values, each rounded
+// exactly like its scalar counterpart
+__device__ __forceinline__ float2 f2bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 // Packed column sums (FADD2 / FFMA2: half the instructions of the scalar versions above).  Lane = 16 * half + pair
 // sums the 16 rows [16 half, 16 half + 16) of the two adjacent columns col2, col2 + 1 (col2 even).  The two halves are
 // separate accumulators until the kernel's final fold.
