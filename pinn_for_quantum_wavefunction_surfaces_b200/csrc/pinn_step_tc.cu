@@ -139,12 +139,15 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
     const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
     const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float u = fmaf(a, w0a[i], fmaf(b, w1a[i], b1a[i]));
-      const float s = sigm(u);
-      const float sp = fmaf(-s, s, s);            // s(1-s)
-      const float spp = fmaf(-2.0f * s, sp, sp);  // s'(1-2s)
-      s_[k4 + i] = s; sp_[k4 + i] = sp; spp_[k4 + i] = spp;
+    for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction; the sigmoid (MUFU) stays scalar
+      const float2 u = f2fma(f2bc(a), make_float2(w0a[i], w0a[i + 1]),
+                             f2fma(f2bc(b), make_float2(w1a[i], w1a[i + 1]), make_float2(b1a[i], b1a[i + 1])));
+      const float2 s = make_float2(sigm(u.x), sigm(u.y));
+      const float2 sp = f2fma(f2neg(s), s, s);                      // s(1-s)
+      const float2 spp = f2fma(f2mul(f2bc(-2.0f), s), sp, sp);      // s'(1-2s)
+      s_[k4 + i] = s.x; s_[k4 + i + 1] = s.y;
+      sp_[k4 + i] = sp.x; sp_[k4 + i + 1] = sp.y;
+      spp_[k4 + i] = spp.x; spp_[k4 + i + 1] = spp.y;
     }
   }
   {
@@ -185,12 +188,14 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       const float q11a[4] = {q11.x, q11.y, q11.z, q11.w};
       float h1[4], h2[4], h3[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const float d1 = fmaf(al1, w0a[i], al2 * w1a[i]);
-        const float q = fmaf(al11, q00a[i], fmaf(al12, q01a[i], al22 * q11a[i]));
-        h1[i] = sp_[k4 + i] * w0a[i];
-        h2[i] = sp_[k4 + i] * w1a[i];
-        h3[i] = fmaf(sp_[k4 + i], d1, spp_[k4 + i] * q);
+      for (int i = 0; i < 4; i += 2) {
+        const float2 w0 = make_float2(w0a[i], w0a[i + 1]), w1 = make_float2(w1a[i], w1a[i + 1]);
+        const float2 sp = make_float2(sp_[k4 + i], sp_[k4 + i + 1]), spp = make_float2(spp_[k4 + i], spp_[k4 + i + 1]);
+        const float2 d1 = f2fma(f2bc(al1), w0, f2mul(f2bc(al2), w1));
+        const float2 q = f2fma(f2bc(al11), make_float2(q00a[i], q00a[i + 1]),
+                               f2fma(f2bc(al12), make_float2(q01a[i], q01a[i + 1]), f2mul(f2bc(al22), make_float2(q11a[i], q11a[i + 1]))));
+        const float2 a1 = f2mul(sp, w0), a2 = f2mul(sp, w1), a3 = f2fma(sp, d1, f2mul(spp, q));
+        h1[i] = a1.x; h1[i + 1] = a1.y; h2[i] = a2.x; h2[i + 1] = a2.y; h3[i] = a3.x; h3[i + 1] = a3.y;
       }
       ST4(&Hrow[(0 * NH + k4) ^ sx], s_[k4], s_[k4 + 1], s_[k4 + 2], s_[k4 + 3]);
       ST4(&Hrow[(1 * NH + k4) ^ sx], h1[0], h1[1], h1[2], h1[3]);
@@ -219,18 +224,20 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
       float tt[4], va[4], vb[4], vD[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction; the sigmoid (MUFU) stays scalar
         const int j = j4 + i;
-        const float v0 = V0[j] + b2a[i], v1 = V1[j], v2 = V2[j];
-        const float v3 = fmaf(al1, v1, fmaf(al2, v2, fmaf(al11, P00[j], fmaf(al12, P01[j], al22 * P11[j]))));
-        const float t = sigm(v0);
-        const float tp = fmaf(-t, t, t);
-        const float tpp = fmaf(-2.0f * t, tp, tp);
-        const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
-        const float gD = fmaf(tp, v3, tpp * Q);
-        accN = fmaf(woa[i], t, accN);
-        accD = fmaf(woa[i], gD, accD);
-        tt[i] = t; va[i] = v1; vb[i] = v2; vD[i] = v3;
+        const float2 v1 = make_float2(V1[j], V1[j + 1]), v2 = make_float2(V2[j], V2[j + 1]);
+        const float2 v3 = f2fma(f2bc(al1), v1, f2fma(f2bc(al2), v2,
+                          f2fma(f2bc(al11), make_float2(P00[j], P00[j + 1]),
+                                f2fma(f2bc(al12), make_float2(P01[j], P01[j + 1]), f2mul(f2bc(al22), make_float2(P11[j], P11[j + 1]))))));
+        const float2 t = make_float2(sigm(V0[j] + b2a[i]), sigm(V0[j + 1] + b2a[i + 1]));
+        const float2 tp = f2fma(f2neg(t), t, t);
+        const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
+        const float2 Q = f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));
+        const float2 gD = f2fma(tp, v3, f2mul(tpp, Q));
+        accN = fmaf(woa[i], t.x, accN); accN = fmaf(woa[i + 1], t.y, accN);
+        accD = fmaf(woa[i], gD.x, accD); accD = fmaf(woa[i + 1], gD.y, accD);
+        tt[i] = t.x; tt[i + 1] = t.y; va[i] = v1.x; va[i + 1] = v1.y; vb[i] = v2.x; vb[i + 1] = v2.y; vD[i] = v3.x; vD[i + 1] = v3.y;
       }
       if (STASH) {
         ST4(&Grow[(0 * NH + j8 + j4) ^ sx], tt[0], tt[1], tt[2], tt[3]);
@@ -280,21 +287,28 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
       const float vba[4] = {bv.x, bv.y, bv.z, bv.w}, vDa[4] = {dv.x, dv.y, dv.z, dv.w};
       const float woa[4] = {wov.x, wov.y, wov.z, wov.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction (FFMA2 / FMUL2)
         const int j = j4 + i;
-        const float t = ta[i], v1 = vaa[i], v2 = vba[i], v3 = vDa[i];
-        const float tp = fmaf(-t, t, t);
-        const float tpp = fmaf(-2.0f * t, tp, tp);
-        const float tppp = tp * fmaf(-6.0f, tp, 1.0f);
-        const float Q = fmaf(al11 * v1, v1, fmaf(al12 * v1, v2, al22 * v2 * v2));
-        const float gD = fmaf(tp, v3, tpp * Q);
-        const float tbar = lamN * woa[i], gDbar = lamD * woa[i];
-        dwo[j] = fmaf(lamN, t, lamD * gD);
-        const float c2 = gDbar * tpp;
-        vbar[3][j] = gDbar * tp;
-        vbar[1][j] = c2 * fmaf(2.0f * al11, v1, al12 * v2);
-        vbar[2][j] = c2 * fmaf(al12, v1, 2.0f * al22 * v2);
-        vbar[0][j] = fmaf(tbar, tp, gDbar * fmaf(tpp, v3, tppp * Q));
+        const float2 t = make_float2(ta[i], ta[i + 1]), v1 = make_float2(vaa[i], vaa[i + 1]);
+        const float2 v2 = make_float2(vba[i], vba[i + 1]), v3 = make_float2(vDa[i], vDa[i + 1]);
+        const float2 wo2 = make_float2(woa[i], woa[i + 1]);
+        const float2 tp = f2fma(f2neg(t), t, t);
+        const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
+        const float2 tppp = f2mul(tp, f2fma(f2bc(-6.0f), tp, f2bc(1.0f)));
+        const float2 Q = f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));
+        const float2 gD = f2fma(tp, v3, f2mul(tpp, Q));
+        const float2 tbar = f2mul(f2bc(lamN), wo2), gDbar = f2mul(f2bc(lamD), wo2);
+        const float2 dw = f2fma(f2bc(lamN), t, f2mul(f2bc(lamD), gD));
+        const float2 c2 = f2mul(gDbar, tpp);
+        const float2 vb3 = f2mul(gDbar, tp);
+        const float2 vb1 = f2mul(c2, f2fma(f2bc(2.0f * al11), v1, f2mul(f2bc(al12), v2)));
+        const float2 vb2 = f2mul(c2, f2fma(f2bc(al12), v1, f2mul(f2bc(2.0f * al22), v2)));
+        const float2 vb0 = f2fma(tbar, tp, f2mul(gDbar, f2fma(tpp, v3, f2mul(tppp, Q))));
+        dwo[j] = dw.x; dwo[j + 1] = dw.y;
+        vbar[3][j] = vb3.x; vbar[3][j + 1] = vb3.y;
+        vbar[1][j] = vb1.x; vbar[1][j + 1] = vb1.y;
+        vbar[2][j] = vb2.x; vbar[2][j + 1] = vb2.y;
+        vbar[0][j] = vb0.x; vbar[0][j + 1] = vb0.y;
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ch++)
