@@ -304,19 +304,19 @@ def main():
             out[8:] = torch.from_numpy(dth_h).to(dev)
             dist.all_reduce(out)
 
-    Ke = max(3, min(K, 50))
-    for i in range(3):
-        e2e_step(i)
+    Ke = max(3, min(K, 200))
+    for i in range(N_BATCHES + 3):   # one pass over every page-locked batch buffer first (the GPU's first touch of a
+        e2e_step(i)                  # host page is slower), then the timed calls
     fence()
     te0 = time.time()
     for i in range(Ke):
-        e2e_step(3 + i)
+        e2e_step(N_BATCHES + 3 + i)
     fence()
     te = (time.time() - te0) / Ke
     e2e_split = h.host_timing()   # of the last call
     h.profile_begin()             # the kernel's share, measured on a few more calls outside the timed loop
     for i in range(10):
-        e2e_step(3 + Ke + i)
+        e2e_step(N_BATCHES + 3 + Ke + i)
     fence()
     e2e_kern_ms, e2e_kern_n = h.profile_collect()
     tte = torch.tensor([te], dtype=torch.float64, device=dev)
