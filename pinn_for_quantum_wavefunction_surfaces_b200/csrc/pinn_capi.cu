@@ -402,6 +402,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: bad in_dtype");
+  std::lock_guard<std::mutex> host_lock(h->host_mu);
   const auto t_enter = std::chrono::steady_clock::now();
   DevGuard dev_guard(h->device);
   const size_t es = in_dtype == PINN_F64 ? 8 : 4;

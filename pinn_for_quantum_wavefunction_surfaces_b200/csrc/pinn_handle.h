@@ -47,6 +47,7 @@ struct pinn_handle {
   size_t ev_used = 0;
   std::string err;
   std::mutex mu;
+  std::mutex host_mu;  // pinn_loss_fwd_bwd_host calls on one handle share its staging / mapped buffers: one at a time
 };
 
 // Every entry point works on the handle's device and leaves the caller's current device as it found it.
