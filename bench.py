@@ -3,10 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P]
 
-A step = one training evaluation (forward + Laplacian + loss + parameter gradients; for N>1 followed
-by the 12 KB gradient all-reduce) of the poc-form ionHsym model on one batch of P synthetic collocation
-points per GPU (default 2^18 = BASELINE config 3; weak scaling: every GPU gets its own P points).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+A step = one training evaluation (forward + Laplacian + loss + parameter gradients; for N>1 including the
+sum of the 8 + 1521 float64 over the ranks, fused into the reduction kernel or, --allreduce nccl, as a
+separate all-reduce) of the poc-form ionHsym model on one batch of P synthetic collocation points per GPU
+(default 2^18 = BASELINE config 3; weak scaling: every GPU gets its own P points).
+Prints ONE JSON line (rank 0): value (device-resident inputs), roofline (kernel events, ncu figures of the
+committed capture), e2e (page-locked host inputs through HostStep / pinn_loss_fwd_bwd_host), and at N=1
+cpu_baseline, reference_autograd_on_gpu, dense_grid_inference, device_train_loop.  See DESIGN.md section 5.
 """
 import argparse
 import json
