@@ -196,3 +196,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["vs_baseline"] is None and line["config"]["workload"].startswith("ionHsym")
+
+
+def test_stash_swizzle_is_conflict_free_for_all_three_access_patterns():
+    """The stash swizzle of the tcgen05 engine (csrc/pinn_device.cuh: swz_tc) restated: a row is one point, 64 floats
+    (every row starts on bank 0); the 16-byte chunk index of row r is XOR-ed with ((r&3)<<1)|((r>>2)&1).  Checked here
+    against the bank model (32 banks x 4 bytes; a 128-bit access is served a quarter-warp at a time, a 64-bit access a
+    half-warp at a time): all three access patterns of the kernel touch every bank at most once per phase."""
+    src = open(os.path.join(ROOT, "pinn_for_quantum_wavefunction_surfaces_b200", "csrc", "pinn_device.cuh")).read()
+    assert "((((row & 3) << 1) | ((row >> 2) & 1)) << 2)" in src      # the formula this test restates
+    swz = lambda r: ((((r & 3) << 1) | ((r >> 2) & 1)) << 2)          # in floats
+    ROW = 64
+    bank = lambda row, col: (row * ROW + (col ^ swz(row))) % 32
+    # (a) every lane reads/writes a float4 of ITS OWN row at the same logical column: 8 lanes per phase
+    for c4 in range(0, ROW, 4):
+        for q in range(4):
+            banks = [bank(l, c4 + k) for l in range(8 * q, 8 * q + 8) for k in range(4)]
+            assert len(set(banks)) == 32, ("row access", c4, q)
+    # (b) mma.sync fragment loads: lane (g, t) reads row p0 + t (or + 4), column c0 + g (or + 8), 32 lanes per phase
+    for p0 in range(0, 32, 8):
+        for dp in (0, 4):
+            for c0 in range(0, ROW, 16):
+                for dc in (0, 8):
+                    banks = [bank(p0 + dp + t, c0 + dc + g) for g in range(8) for t in range(4)]
+                    assert len(set(banks)) == 32, ("fragment", p0, dp, c0, dc)
+    # (c) packed column sums: 16 lanes of a half-warp read float2 (columns 2 cp, 2 cp + 1) of ONE row per phase
+    for row in range(32):
+        for win in (0, 16, 48):   # the three 32-column windows used (wrapping at 64)
+            banks = [bank(row, ((win + 2 * cp) & 63) + k) for cp in range(16) for k in range(2)]
+            assert len(set(banks)) == 32, ("column sum", row, win)
+    # ... and the swizzle it replaced was 2-way conflicted on (a): documented in DESIGN.md
+    old = lambda r: (r & 3) << 3
+    banks = [(l * ROW + (0 ^ old(l)) + k) % 32 for l in range(8) for k in range(4)]
+    assert len(set(banks)) == 16
