@@ -188,6 +188,21 @@ def run_reference(args):
     }))
 
 
+def hbm_ceiling(bytes_per_launch, kernel_ms):
+    """The contract's other denominator: the kernel against the measured HBM copy rate (MEASURED_PEAKS.json, burst figure for
+    a kernel timed alone; the profiling recipe's 6650 GB/s "of fallback" when the file is absent).  27 kFLOP per 16 bytes puts this path
+    three orders of magnitude on the compute side of the ridge, which is why `bound` is the FP32 pipe."""
+    peak, src = 6650.0, "of fallback (B200_PROFILING.md)"
+    pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pj):
+        try:
+            peak, src = float(json.load(open(pj))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    ach = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,7 +401,8 @@ def main():
                          "flop_per_point": FLOP_PER_POINT, "engine": args.engine,
                          "kernel": "pinn_step_tc_kernel<2,true>" if args.engine == "tcgen05" else "pinn_step_kernel<2,4,true>",
                          "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes},
+                         "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes,
+                         "vs_hbm_ceiling": hbm_ceiling(16 * n, kern_avg_ms)},
             "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
                     "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke, "kernel_ms": e2e_kern_ms / max(e2e_kern_n, 1),
                     "last_call_us": {k: round(v, 1) for k, v in e2e_split.items()},
