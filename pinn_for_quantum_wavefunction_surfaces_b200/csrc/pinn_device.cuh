@@ -49,7 +49,9 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
 //  * weights (split once per step by prep_weights_kernel): split_tf32_rn - hi is x ROUNDED to nearest TF32 (add half an
 //    ulp, clear the low 13 bits), lo = x - hi is exact in fp32 and gets half an ulp added so that the hardware truncation
 //    rounds it to nearest as well: |lo| <= 2^-11 |x| with random sign.
-//  * activations (split per point in the hot loops): split_tf32 - two instructions, hi = the 19 bits the hardware would
+//  * forward-sweep activations: split_tf32_rn3 - the same rounded hi, lo = x - hi left as it is (three instructions): the
+//    hardware truncates lo's last one or two bits toward zero, <= 2^-22 |x| and unbiased since lo has a random sign.
+//  * reverse-sweep activations and weight-gradient fragments: split_tf32 - two instructions, hi = the 19 bits the hardware would
 //    read anyway, lo = x - hi exact (the low 13 mantissa bits; the hardware keeps 11 significant bits of them, i.e. loses
 //    at most 2^-22 |x|).  The dropped lo*lo term is <= 2^-21 of the product with the sign of the weight's lo, i.e.
 //    unbiased in the mat-vecs; in the weight-gradient contractions (both operands are activations) it is a common factor
@@ -61,6 +63,10 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 __device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void split_tf32_rn3(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
