@@ -31,6 +31,7 @@ struct alignas(128) Wts {
   float bE2[NE], wE[NE];
   float WgL[12], bgL[12], wg[12];        // 10 used
   float bo, bE, bg, pad0;
+  float w0s[NH], w1s[NH], b1s[NH], b2s[NH];  // w0, w1, b1, b2 times -log2(e): pre-activations arrive as the MUFU.EX2 argument
   float pad1[24];                        // keeps the operand images below 128-byte aligned
   // ---- tcgen05 B operands (pinn_step_tc.cu): [hi | lo] TF32 split, K-major canonical no-swizzle layout
   //      (8-row x 16-byte core matrices; see umma_off()) ----

@@ -38,6 +38,13 @@ __device__ __forceinline__ float sigm(float u) {
   return rcp_approx(1.0f + e);
 }
 
+constexpr float NEG_LOG2E = -1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
@@ -237,6 +244,8 @@ __device__ __forceinline__ void build_weight_image(const float* __restrict__ th,
     out->w0[i] = a; out->w1[i] = b; out->b1[i] = th[O_B1 + i];
     out->ww00[i] = a * a; out->ww01[i] = a * b; out->ww11[i] = b * b;
     out->b2[i] = th[O_B2 + i]; out->wo[i] = th[O_WO + i];
+    out->w0s[i] = a * NEG_LOG2E; out->w1s[i] = b * NEG_LOG2E;
+    out->b1s[i] = th[O_B1 + i] * NEG_LOG2E; out->b2s[i] = th[O_B2 + i] * NEG_LOG2E;
   }
   for (int i = t; i < NE; i += nt) {
     out->WE1[i] = th[O_WE1 + i]; out->bE1[i] = th[O_BE1 + i];
@@ -308,6 +317,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// two sigmoids whose arguments already carry the factor -log2(e) (pre-scaled weights, Wts::w0s ...): 2 MUFU.EX2, one packed
+// add, 2 MUFU.RCP
+__device__ __forceinline__ float2 sigm2_pre(const float2 up) {
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(up.x), ex2_approx(up.y)), make_float2(1.0f, 1.0f));
+  return make_float2(rcp_approx(d.x), rcp_approx(d.y));
 }
 
 #define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))

@@ -135,14 +135,14 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
   float s_[NH], sp_[NH], spp_[NH];
 #pragma unroll
   for (int k4 = 0; k4 < NH; k4 += 4) {
-    const float4 w0v = LD4(&w.w0[k4]), w1v = LD4(&w.w1[k4]), b1v = LD4(&w.b1[k4]);
+    const float4 w0v = LD4(&w.w0s[k4]), w1v = LD4(&w.w1s[k4]), b1v = LD4(&w.b1s[k4]);  // times -log2(e)
     const float w0a[4] = {w0v.x, w0v.y, w0v.z, w0v.w}, w1a[4] = {w1v.x, w1v.y, w1v.z, w1v.w};
     const float b1a[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-    for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction; the sigmoid (MUFU) stays scalar
+    for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction; u = -log2(e) * pre-activation, one rounding
       const float2 u = f2fma(f2bc(a), make_float2(w0a[i], w0a[i + 1]),
                              f2fma(f2bc(b), make_float2(w1a[i], w1a[i + 1]), make_float2(b1a[i], b1a[i + 1])));
-      const float2 s = make_float2(sigm(u.x), sigm(u.y));
+      const float2 s = sigm2_pre(u);
       const float2 sp = f2fma(f2neg(s), s, s);                      // s(1-s)
       const float2 spp = f2fma(f2mul(f2bc(-2.0f), s), sp, sp);      // s'(1-2s)
       s_[k4 + i] = s.x; s_[k4 + i + 1] = s.y;
@@ -220,7 +220,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
     tc_wait_ld(V0); tc_wait_ld(V1); tc_wait_ld(V2); tc_wait_ld(P00); tc_wait_ld(P01); tc_wait_ld(P11);
 #pragma unroll
     for (int j4 = 0; j4 < 8; j4 += 4) {
-      const float4 b2v = LD4(&w.b2[j8 + j4]), wov = LD4(&w.wo[j8 + j4]);
+      const float4 b2v = LD4(&w.b2s[j8 + j4]), wov = LD4(&w.wo[j8 + j4]);
       const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
       float tt[4], va[4], vb[4], vD[4];
 #pragma unroll
@@ -230,7 +230,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
         const float2 v3 = f2fma(f2bc(al1), v1, f2fma(f2bc(al2), v2,
                           f2fma(f2bc(al11), make_float2(P00[j], P00[j + 1]),
                                 f2fma(f2bc(al12), make_float2(P01[j], P01[j + 1]), f2mul(f2bc(al22), make_float2(P11[j], P11[j + 1]))))));
-        const float2 t = make_float2(sigm(V0[j] + b2a[i]), sigm(V0[j + 1] + b2a[i + 1]));
+        const float2 t = sigm2_pre(f2fma(make_float2(V0[j], V0[j + 1]), f2bc(NEG_LOG2E), make_float2(b2a[i], b2a[i + 1])));
         const float2 tp = f2fma(f2neg(t), t, t);
         const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
         const float2 Q = f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));

@@ -5,7 +5,9 @@ Tolerances (BASELINE.json north_star): psi, laplacian, residual: 1e-5 norm-relat
 (max|a-b| / max|b|); loss: 1e-5 relative.  Parameter gradients: 1e-5 norm-relative per tensor at
 generic (random-init) weights.  At the shipped *trained* weights the gradient is a cancelling sum
 (|res| ~ 1e-3 of its terms, psi at the boundary ~1e-8 from O(0.1) terms), so ANY float32 evaluation
-is limited there: torch's own float32 autograd reaches 1.4e-4 (measured); the bar used is 2e-3.
+is limited there: torch's own float32 autograd reaches 1.4e-4 (measured).  The tcgen05 engine feeds MUFU.EX2
+with pre-activations that carry -log2(e) inside a single FMA rounding and measures 3e-5 there (bar 2e-4); the FFMA
+engine (plain u * -log2(e)) measures 5e-4 ... 8e-4 (bar 2e-3).
 """
 import os
 
@@ -34,6 +36,11 @@ def engine(request):
     h.set_engine(request.param)
     yield request.param
     h.set_engine("tcgen05")
+
+
+def trained_bar(engine):
+    """gradient bar at the shipped trained weights (module docstring)"""
+    return 2e-4 if engine == "tcgen05" else 2e-3
 
 
 def rel(a, b):
@@ -92,7 +99,7 @@ def check_tensors(dth, ref, tol):
 
 
 # ---------------------------------------------------------------------------------------------
-def test_golden_reference_outputs_poc(golden_dir, ck):
+def test_golden_reference_outputs_poc(golden_dir, ck, engine):
     """CUDA path vs outputs of the REAL reference (NN_ion.LossFunctions + backward, fp64) on its own points."""
     g = np.load(os.path.join(golden_dir, "poc_seed0_n4096.npz"))
     n = g["x"].size
@@ -104,9 +111,10 @@ def test_golden_reference_outputs_poc(golden_dir, ck):
         ref = g[tag + "_loss"]
         assert abs(sums[0] - ref[0]) / ref[0] < 1e-5
         assert abs(sums[1] - ref[1]) / ref[1] < 1e-5
-        assert abs(sums[2] - ref[2]) / ref[2] < 5e-3  # Lbc ~ 9e-10: psi^2 of a 1e-8 cancellation, fp32-limited
+        # Lbc ~ 9e-10: psi^2 of a 1e-8 cancellation, fp32-limited
+        assert abs(sums[2] - ref[2]) / ref[2] < (5e-4 if engine == "tcgen05" else 5e-3)
         assert rel(E, g[tag + "_E"]) < 1e-5
-        assert rel(dth, g[tag + "_grad"]) < 2e-3
+        assert rel(dth, g[tag + "_grad"]) < trained_bar(engine)
         t = lambda a: torch.from_numpy(a).to(dev())
         f = pk.fields("poc", *[t(a) for a in a64], t(th32))
         torch.cuda.synchronize()
@@ -151,14 +159,14 @@ def test_loss_and_grad_vs_oracle_ragged_sizes(variant, n, init_theta):
     check_tensors(dth, ref["grad"], 1e-5)
 
 
-def test_trained_weights_vs_oracle(ck):
+def test_trained_weights_vs_oracle(ck, engine):
     a32, m1, m2 = sample(0, 8192, 3)
     th32 = ck["ionHsym"].astype(np.float32)
     ref = oracle(0, th32, a32, m1, m2)
     sums, dth, E = run_gpu(0, a32, th32, m1, m2)
     assert abs(sums[0] - ref["Ltot"]) / ref["Ltot"] < 1e-5
     assert abs(sums[1] - ref["Lpde"]) / ref["Lpde"] < 1e-5
-    assert rel(dth, ref["grad"]) < 2e-3  # fp32 cancellation limit, see module docstring
+    assert rel(dth, ref["grad"]) < trained_bar(engine)  # fp32 cancellation limit, see module docstring
     # E-net and gate gradients do not pass through the cancelling output layer: tight
     for i in range(6, 16):
         assert rel(dth[OFFS[i]:OFFS[i + 1]], ref["grad"][OFFS[i]:OFFS[i + 1]]) < 2e-5
