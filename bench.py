@@ -176,7 +176,7 @@ def run_reference(args):
     dt = (time.time() - t0) / steps
     v = ns / dt
     sample = "each step = %d-point sample of the 2^18-point batch; float64 nested autograd (oracle/ref_autograd.py)" % ns
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "collocation points/sec per training step (fwd+lap+bwd)", "value": v,
         "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -185,7 +185,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def hbm_ceiling(bytes_per_launch, kernel_ms):
@@ -203,7 +203,27 @@ def hbm_ceiling(bytes_per_launch, kernel_ms):
     return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src}
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries below us write there too (NCCL prints its version banner on
+    communicator creation when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the
+    whole run and the result line goes to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -415,7 +435,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if fused:
         h.dp_status()
         dp.detach_fused(h)
