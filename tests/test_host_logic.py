@@ -188,6 +188,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
+    assert len(r.stdout.strip().splitlines()) == 1, r.stdout  # ONE line on stdout
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
@@ -229,3 +230,16 @@ def test_stash_swizzle_is_conflict_free_for_all_three_access_patterns():
     old = lambda r: (r & 3) << 3
     banks = [(l * ROW + (0 ^ old(l)) + k) % 32 for l in range(8) for k in range(4)]
     assert len(set(banks)) == 16
+
+
+def test_bench_keeps_library_banners_off_stdout():
+    """Whatever a library writes to file descriptor 1 during the run (NCCL's version banner, for one) lands on stderr; the
+    result line alone reaches the caller's stdout."""
+    import json
+    import subprocess
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'NCCL version x\\n'); "
+            "print('python-level chatter'); bench.emit({'metric': 'm', 'value': 1.0})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert json.loads(r.stdout) == {"metric": "m", "value": 1.0}
+    assert "NCCL version x" in r.stderr and "python-level chatter" in r.stderr
