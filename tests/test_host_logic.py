@@ -243,3 +243,29 @@ def test_bench_keeps_library_banners_off_stdout():
     assert r.returncode == 0, r.stderr[-2000:]
     assert json.loads(r.stdout) == {"metric": "m", "value": 1.0}
     assert "NCCL version x" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_tf32_split_model_rounding_and_bias():
+    """Bit-level numpy model of the three x = hi + lo splits in csrc/pinn_device.cuh (the tensor core reads the upper 19
+    bits of each operand): every split is exact in fp32; what the hardware sees of (hi, lo) is within 2^-21.4 |x|
+    (truncating split, always toward zero: a bias) or 2^-23 |x| (rounded hi, with or without the half-ulp pre-rounding of
+    lo: the three-instruction form loses nothing against the four-instruction one, and neither is biased)."""
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(1 << 18) * np.exp(rng.uniform(-8, 3, 1 << 18))).astype(np.float32)
+    bits = lambda a: a.view(np.uint32)
+    seen_by_mma = lambda a: (bits(a) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    def split(x, round_hi, round_lo):
+        hi = ((bits(x) + np.uint32(0x1000 if round_hi else 0)) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = (x - hi).astype(np.float32)
+        assert np.all(hi.astype(np.float64) + lo.astype(np.float64) == x.astype(np.float64))  # exact
+        if round_lo:
+            lo = (bits(lo) + np.uint32(0x1000)).view(np.float32)
+        seen = seen_by_mma(hi).astype(np.float64) + seen_by_mma(lo).astype(np.float64)
+        return (seen - x.astype(np.float64)) / x.astype(np.float64)   # signed relative error
+
+    e_trunc, e_rn3, e_rn4 = split(x, False, False), split(x, True, False), split(x, True, True)
+    assert np.abs(e_trunc).max() < 2.0 ** -21 and e_trunc.max() <= 0.0 and e_trunc.mean() < -5e-8   # one-sided
+    for e in (e_rn3, e_rn4):
+        assert np.abs(e).max() <= 2.0 ** -23 and abs(e.mean()) < 2e-9                                # unbiased
+    assert np.abs(e_rn3).max() == np.abs(e_rn4).max()
