@@ -93,7 +93,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 }
 // split 16 values and store them as the hi / lo halves of an A operand row.  RN: the round-to-nearest split of the
 // activations (three instructions, split_tf32_rn3: measured as accurate as the four-instruction form, -1.5 % time; forward
-// sweep: psi ~ 1e-8 at the boundary is a cancellation of O(0.1) terms, a common rounding direction of all points would
+// sweep: psi ~ 2e-5 at the boundary is a cancellation of O(0.1) terms, a common rounding direction of all points would
 // add up in the loss and its gradient); otherwise the two-instruction truncating split (reverse sweep: a common factor
 // 1 - O(2^-22) on a gradient is harmless).  See split_tf32 in pinn_device.cuh.
 template <bool RN>
