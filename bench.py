@@ -222,6 +222,24 @@ def emit(line):
     _RESULT_OUT.flush()
 
 
+def tensor_ceiling(flop_per_launch, kernel_ms):
+    """SURVEY section 8(d)'s denominator for contractions moved to the tensor pipe: the measured dense tensor rate in TF32
+    (= half the bf16 figure of MEASURED_PEAKS.json, burst, for a kernel timed alone; 1590 TFLOP/s bf16 "of fallback"
+    without the file) divided by 3 for 3xTF32.  The numerator is the canonical FLOP count of the WHOLE step, of which about
+    half (layer-2 mat-vecs of the MLP and the E-net, forward and reverse) runs on tcgen05; ncu's tensor-pipe utilisation
+    (roofline.ncu_pipe_utilisation_pct.tensor) is the direct measurement."""
+    bf16, src = 1590.0, "of fallback (B200_PROFILING.md)"
+    pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pj):
+        try:
+            bf16, src = float(json.load(open(pj))["bf16_tflops"]), "of measured (MEASURED_PEAKS.json bf16_tflops / 2 / 3)"
+        except (KeyError, ValueError):
+            pass
+    peak = bf16 / 2.0 / 3.0
+    ach = flop_per_launch / (kernel_ms * 1e-3) / 1e12
+    return {"achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -422,7 +440,8 @@ def main():
                          "kernel": "pinn_step_tc_kernel<2,true>" if args.engine == "tcgen05" else "pinn_step_kernel<2,4,true>",
                          "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic,
                          "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes,
-                         "vs_hbm_ceiling": hbm_ceiling(16 * n, kern_avg_ms)},
+                         "vs_hbm_ceiling": hbm_ceiling(16 * n, kern_avg_ms),
+                         "vs_3xtf32_tensor_ceiling": tensor_ceiling(FLOP_PER_POINT * n, kern_avg_ms)},
             "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
                     "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke, "kernel_ms": e2e_kern_ms / max(e2e_kern_n, 1),
                     "last_call_us": {k: round(v, 1) for k, v in e2e_split.items()},

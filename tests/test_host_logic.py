@@ -269,3 +269,18 @@ def test_tf32_split_model_rounding_and_bias():
     for e in (e_rn3, e_rn4):
         assert np.abs(e).max() <= 2.0 ** -23 and abs(e.mean()) < 2e-9                                # unbiased
     assert np.abs(e_rn3).max() == np.abs(e_rn4).max()
+
+
+def test_bench_roofline_denominators():
+    """The two contract ceilings bench.py reports beside the FP32 one: measured HBM copy rate and measured tensor rate in
+    3xTF32 (MEASURED_PEAKS.json when present, the profiling recipe's fallbacks otherwise)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n, ms = 1 << 18, 0.1167
+    hb = bench.hbm_ceiling(16 * n, ms)
+    tc = bench.tensor_ceiling(27044.0 * n, ms)
+    assert hb["unit"] == "GB/s" and abs(hb["achieved"] - 16 * n / (ms * 1e-3) / 1e9) < 1e-9
+    assert 5000.0 < hb["peak"] < 8000.0 and abs(hb["frac"] - hb["achieved"] / hb["peak"]) < 1e-12
+    assert tc["unit"] == "TFLOP/s" and abs(tc["achieved"] - 27044.0 * n / (ms * 1e-3) / 1e12) < 1e-9
+    assert 200.0 < tc["peak"] < 400.0 and abs(tc["frac"] - tc["achieved"] / tc["peak"]) < 1e-12
+    assert "measured" in hb["peak_source"] or "fallback" in hb["peak_source"]
