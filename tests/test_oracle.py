@@ -41,6 +41,17 @@ def test_enet_matches_reference_pkl(golden_dir):
     assert abs(E[0] - (-1.62905384)) < 1e-8
 
 
+def test_enet_against_exact_h2plus_energies(golden_dir):
+    """Physics pin (exactE() poc/main.py:48-61): the E-net of the shipped fine-tuned model against the tabulated
+    exact electronic energies of H2+ (Hartree) at internuclear distance D = 2R: within 6.4e-3 for R >= 1, 3.1e-3 for R >= 2."""
+    exact = {2.0: -1.1026342, 3.0: -0.9108962, 4.0: -0.7960849, 6.0: -0.6786357, 8.0: -0.6275704}
+    ck = np.load(os.path.join(golden_dir, "checkpoints.npz"))
+    R = np.array([d / 2 for d in exact])
+    E, _ = cf.enet_fwd(layout.unpack_poc(ck["ionHsym_fineTune"]), R)
+    err = np.abs(E - np.array(list(exact.values())))
+    assert err.max() < 6.5e-3 and err[R >= 2.0].max() < 3.2e-3
+
+
 def test_poc_oracles_match_reference_outputs(golden_dir):
     ck = np.load(os.path.join(golden_dir, "checkpoints.npz"))
     g = np.load(os.path.join(golden_dir, "poc_seed0_n4096.npz"))
