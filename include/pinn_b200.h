@@ -11,12 +11,20 @@
  *  - every entry returns 0 on success, a positive cudaError_t value for CUDA
  *    failures and a negative PINN_E* code for argument errors; the message is
  *    available from pinn_last_error().  Nothing throws across this boundary.
- *  - all device buffers are owned by the caller; the library only owns the
- *    workspace allocated in pinn_create().  No allocation happens per call, so
- *    every *device* entry point is CUDA-graph capturable.
+ *  - all device buffers are owned by the caller; the library only owns small
+ *    workspaces (per-CTA partial sums, set counters): ONE PER STREAM that calls in,
+ *    allocated on the first call on that stream.  No allocation happens on later
+ *    calls, so every *device* entry point is CUDA-graph capturable once one plain
+ *    call has been made on the capturing stream.
  *  - every call takes the stream explicitly (as a void* holding a cudaStream_t) and
  *    selects the handle's device itself, so it may be called from any host thread
- *    (torch runs autograd.Function.backward on its own thread).
+ *    (torch runs autograd.Function.backward on its own thread).  Calls on ONE stream
+ *    are ordered by the stream; calls on DIFFERENT streams of one handle (torch's
+ *    current stream, a pinn_trainer's own stream, the *_host entry's private stream)
+ *    may overlap on the device - they share no scratch memory.  Exception: with the
+ *    data-parallel exchange enabled (pinn_dp_*) the handle carries one sequence of
+ *    exchange steps; a call on another stream than the previous exchanging call
+ *    first waits on the host for that stream to drain.
  *  - theta is the packed parameter vector, 1521 scalars in NN_ion.state_dict() order
  *    with nn.Linear (out,in) layout (poc/main.py:233-245):
  *      W1(16,2) b1(16) W2(16,16) b2(16) wo(16) bo | WE1(32) bE1(32) WE2(32,32) bE2(32)
@@ -57,8 +65,8 @@ int pinn_theta_size(void);
 /* Offsets (in scalars) of the 16 tensors inside theta; out must hold 17 ints (last = 1521). */
 void pinn_theta_offsets(int* out);
 
-/* Create a handle bound to CUDA device `device`; allocates the small workspace
- * (prepared weights, per-CTA partial sums, pinned staging for the *_host entry). */
+/* Create a handle bound to CUDA device `device`; allocates the *_host entry's stream, its workspace and its
+ * page-locked result buffer.  Fails with PINN_ENOTSUP on anything but an sm_100 device (there is no fallback). */
 int pinn_create(int device, pinn_handle** out);
 int pinn_destroy(pinn_handle* h);
 /* Message of the last failure on this handle (or of the last pinn_create failure when h==NULL). */
@@ -66,10 +74,10 @@ const char* pinn_last_error(pinn_handle* h);
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t pinn_launch_count(pinn_handle* h);
 
-/* Which implementation of the fused step kernel runs (same results to fp32 rounding, same interface):
- *  PINN_ENGINE_TCGEN05 (default) - skinny mat-vecs as M=128 TF32 tcgen05.mma with activations in tensor memory (3xTF32);
- *  PINN_ENGINE_FFMA              - the same mat-vecs as FFMA chains (kept for A/B measurement).
- * The environment variable PINN_B200_ENGINE=ffma|tcgen05 selects the initial value at pinn_create. */
+/* The library carries ONE implementation of the fused step kernel, PINN_ENGINE_TCGEN05 (skinny mat-vecs as M=128 TF32
+ * tcgen05.mma with activations in tensor memory, 3xTF32); pinn_set_engine(PINN_ENGINE_FFMA) returns PINN_ENOTSUP.  The
+ * FFMA engine (the same mat-vecs as FFMA chains, the round-1 baseline of DESIGN.md section 3) only exists in the separate
+ * A/B build made by tools/build_ab.sh (-DPINN_AB_BUILD), where the two calls below - and nothing else - select it. */
 #define PINN_ENGINE_FFMA 0
 #define PINN_ENGINE_TCGEN05 1
 int pinn_set_engine(pinn_handle* h, int engine);
@@ -129,11 +137,15 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n,
 
 /*
  * Same as pinn_loss_fwd_bwd but with HOST buffers (the call a CPU-resident caller such
- * as the unmodified reference training loop makes): copies the coordinates host->device
- * in up to 4 chunks on a copy stream so that copies overlap the kernels (when weights_host is given), runs the step, copies the 8 sums
- * and 1521 gradients back and synchronises.  theta_host is 1521 double (the reference keeps
- * parameters in float64); weights_host is 3 double or NULL.  Pinned host memory is faster but
- * not required.
+ * as the unmodified reference training loop makes), synchronous.  Page-locked inputs
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) are read by the step kernel IN PLACE
+ * over PCIe, one super-tile ahead of the computation - nothing is copied first; theta and
+ * the loss weights travel inside the kernel parameters; the 8 sums and 1521 gradients are
+ * written by the reduction kernel into mapped page-locked memory and handed back after one
+ * stream synchronisation.  Pageable inputs are staged instead: host->device copies in up
+ * to 4 chunks on a copy stream that overlap the kernels (when weights_host is given).
+ * theta_host is 1521 double (the reference keeps parameters in float64); weights_host is
+ * 3 double or NULL (NULL: the boundary sets are counted on the device first).
  */
 int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n,
                            const void* x, const void* y, const void* z, const void* R, int in_dtype,
@@ -230,6 +242,10 @@ typedef struct pinn_train_config {
 typedef struct pinn_trainer pinn_trainer;
 int pinn_trainer_create(pinn_handle* h, const pinn_train_config* cfg, const double* theta0_host, pinn_trainer** out);
 int pinn_trainer_destroy(pinn_trainer* t);
+/* Resume: parameters, Adam moments (NULL = zeros), optimizer steps already done (Adam's bias correction, the resampling
+ * schedule and best_after keep counting from `step`).  The best-model record restarts (best_theta = theta, best loss back
+ * to its initial limit, best_step = -1), the history restarts at row 0, and for best_mode 0 the first step after the
+ * resume is taken unconditionally like the first step of a fresh run (train.py:58). */
 int pinn_trainer_load_state(pinn_trainer* t, const double* theta, const double* m, const double* v, int64_t step);
 int pinn_trainer_set_batch(pinn_trainer* t, const float* x, const float* y, const float* z, const float* R, const uint8_t* mask,
                            const double* weights_host);

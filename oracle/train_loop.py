@@ -38,8 +38,10 @@ def oracle_trainpy_op(x, y, z, R, i1, i2, *params):
     return F.apply(*params)
 
 
-def trainpy_run(loss_op, n=10000, epochs=1000, lr=8e-3, seed=12345, log=None):
-    """Returns (params tuple in train.py layout with the best parameters restored, trace lines, history array)."""
+def trainpy_run(loss_op, n=10000, epochs=1000, lr=8e-3, seed=12345, log=None, snapshots=None):
+    """Returns (params tuple in train.py layout with the best parameters restored, trace lines, history array).
+    snapshots: optional dict, filled with {tt: canonical packed parameters the loss of step tt was evaluated with} for
+    every tt it already has as a key (drift curves of a float32 loss against the float64 one)."""
     dtype = torch.double
     torch.manual_seed(seed)                                   # train.py:74
     bcutoff, cutoff, L, Rlo, Rhi, sc_sampling = 17.5, 0.005, 18, 0.2, 3, 1   # train.py:78-84
@@ -74,6 +76,8 @@ def trainpy_run(loss_op, n=10000, epochs=1000, lr=8e-3, seed=12345, log=None):
                 r2sq = (x + R) ** 2 + y ** 2 + z ** 2
                 i1, = torch.where(r1sq[:, 0] >= bcutoff ** 2)
                 i2, = torch.where(r2sq[:, 0] >= bcutoff ** 2)
+        if snapshots is not None and tt in snapshots:
+            snapshots[tt] = layout.from_trainpy([p.detach().numpy().copy() for p in params])
         Ltot, Lpde, Lbc, e = loss_op(x, y, z, R, i1, i2, *params)
         lt = float(Ltot.detach())
         if tt == 0 or lt < Lbest:

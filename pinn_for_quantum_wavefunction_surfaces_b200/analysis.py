@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from ._lib import Handle, PinnError
+from .params import check_supported_model
 
 _DEFAULTS = {"xL": -18, "xR": 18, "yL": -18, "yR": 18, "zL": -18, "zR": 18, "RxL": 0.2, "RxR": 4, "n_test": 80}
 
@@ -58,6 +59,7 @@ def grid_sums(theta, Ri, params=None, variant="poc", n=None, rule="avg", device=
         raise PinnError("no CUDA device: the PINN hot path has no CPU fallback")
     pr = dict(_DEFAULTS)
     pr.update(params or {})
+    check_supported_model(pr)
     n = pr["n_test"] if n is None else n
     nx, ny, nz = (n, n, n) if np.isscalar(n) else n
     h = Handle.get(torch.cuda.current_device() if device is None else device)

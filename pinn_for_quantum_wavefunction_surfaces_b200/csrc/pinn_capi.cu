@@ -50,7 +50,7 @@ int pinn_create(int device, pinn_handle** out) {
   pinn_handle* h = new pinn_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  h->max_rows = h->sm_count * 8;
+#ifdef PINN_AB_BUILD  // A/B builds only (tools/build_ab.sh): the product has one engine and reads no environment
   if (const char* e = getenv("PINN_B200_ENGINE")) {
     if (!strcmp(e, "ffma")) h->engine = PINN_ENGINE_FFMA;
     else if (!strcmp(e, "tcgen05")) h->engine = PINN_ENGINE_TCGEN05;
@@ -58,14 +58,10 @@ int pinn_create(int device, pinn_handle** out) {
   if (const char* e = getenv("PINN_B200_HOST_ZEROCOPY")) h->host_zero_copy = strcmp(e, "0") != 0;
   if (const char* e = getenv("PINN_B200_HOST_INLINE")) h->host_inline_params = strcmp(e, "0") != 0;
   CREATE_CU(cudaMalloc(&h->wts, sizeof(Wts)));
+#endif
   // theta (1536 float) and the 3 loss weights share one block so that the *_host entry uploads both with one copy
   CREATE_CU(cudaMalloc(&h->theta_dev, HOST_IN_BYTES));
   h->weights_dev = reinterpret_cast<double*>(h->theta_dev + HOST_IN_THETA);
-  CREATE_CU(cudaMalloc(&h->counts, 2 * sizeof(unsigned long long)));
-  CREATE_CU(cudaMalloc(&h->partials, (size_t)h->max_rows * NPART * sizeof(double)));
-  CREATE_CU(cudaMalloc(&h->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double)));
-  CREATE_CU(cudaMalloc(&h->batch_counter, 2 * sizeof(unsigned long long)));  // [0] batch index of pinn_sample, [1] its block ticket
-  CREATE_CU(cudaMemset(h->batch_counter, 0, 2 * sizeof(unsigned long long)));
   CREATE_CU(cudaHostAlloc(&h->out_pinned, NPART * sizeof(double), cudaHostAllocMapped));
   CREATE_CU(cudaHostGetDevicePointer(&h->out_mapped, h->out_pinned, 0));
   CREATE_CU(cudaMallocHost(&h->theta_pinned, HOST_IN_BYTES));
@@ -74,9 +70,91 @@ int pinn_create(int device, pinn_handle** out) {
   CREATE_CU(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
   CREATE_CU(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   for (int c = 0; c < 4; c++) CREATE_CU(cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+  // the workspace of the *_host entry's stream holds the rows of up to 4 chunk launches
+  if (!ws_for(h, h->s_main, 4 * h->sm_count)) {
+    const std::string msg = h->err;
+    pinn_destroy(h);
+    g_create_err = "pinn_create: " + msg;
+    return PINN_EINVAL;
+  }
   *out = h;
   return 0;
 }
+
+}  // extern "C"
+
+static void ws_free(pinn_workspace& w) {
+  cudaFree(w.partials); cudaFree(w.weights); cudaFree(w.counts); cudaFree(w.grid_partials);
+  w = pinn_workspace();
+}
+
+pinn_workspace* ws_for(pinn_handle* h, cudaStream_t st, int rows) {
+  constexpr size_t MAX_WS = 32;
+  pinn_workspace* w = nullptr;
+  for (pinn_workspace& c : h->ws)
+    if (c.stream == st && c.partials) { w = &c; break; }
+  if (w && w->rows >= rows) {
+    w->last_use = ++h->ws_clock;
+    return w;
+  }
+  // first call on this stream (or more rows than before): allocate.  Not possible while the stream is being captured
+  // into a CUDA graph - the caller has to make one plain call first.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  if (cap != cudaStreamCaptureStatusNone) {
+    fail(h, PINN_EINVAL, "first call on a stream under CUDA-graph capture: call once on this stream outside the capture first");
+    return nullptr;
+  }
+  if (!w) {
+    if (h->ws.size() >= MAX_WS) {  // streams come and go in the caller: recycle the least recently used workspace
+      size_t lru = 0;
+      for (size_t i = 1; i < h->ws.size(); i++)
+        if (h->ws[i].last_use < h->ws[lru].last_use) lru = i;
+      cudaDeviceSynchronize();      // its last kernels may still be running
+      ws_free(h->ws[lru]);
+      w = &h->ws[lru];
+    } else {
+      h->ws.emplace_back();
+      w = &h->ws.back();
+    }
+  } else {
+    cudaStreamSynchronize(st);
+    ws_free(*w);
+  }
+  w->stream = st;
+  cudaError_t e = cudaMalloc(&w->partials, (size_t)rows * NPART * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->weights, 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&w->counts, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(w->counts, 0, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&w->grid_partials, (size_t)(h->sm_count + 1) * 8 * sizeof(double));
+  if (e != cudaSuccess) {
+    ws_free(*w);
+    fail(h, (int)e, "workspace allocation (cudaMalloc)");
+    return nullptr;
+  }
+  w->rows = rows;
+  w->last_use = ++h->ws_clock;
+  return w;
+}
+
+// With the data-parallel exchange enabled the handle's exchange buffers carry one sequence of steps: calls must reach the
+// device in one order on all ranks.  A call on another stream than the previous exchanging call first waits (on the
+// host) for that stream to drain.
+static int dp_serialize(pinn_handle* h, cudaStream_t st) {
+  if (!h->dp_on || h->dp.world <= 1) return 0;
+  if (h->dp_stream_set && h->dp_stream != st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(h, PINN_EINVAL, "data-parallel exchange: the previous exchanging call used another stream; cannot switch streams under capture");
+    CU(h, cudaStreamSynchronize(h->dp_stream));
+  }
+  h->dp_stream = st;
+  h->dp_stream_set = true;
+  return 0;
+}
+
+extern "C" {
 
 static void dp_release(pinn_handle* h) {
   for (int r = 0; r < DP_MAX_WORLD; r++) {
@@ -88,14 +166,19 @@ static void dp_release(pinn_handle* h) {
   h->dp_buf = nullptr;
   h->dp = DpArgs();
   h->dp_on = false;
+  h->dp_stream_set = false;
 }
 
 int pinn_destroy(pinn_handle* h) {
   if (!h) return 0;
   DevGuard dev_guard(h->device);
   dp_release(h);
-  cudaFree(h->wts); cudaFree(h->theta_dev); cudaFree(h->counts);
-  cudaFree(h->partials); cudaFree(h->stage_dev); cudaFree(h->grid_partials); cudaFree(h->batch_counter);
+  cudaDeviceSynchronize();
+#ifdef PINN_AB_BUILD
+  cudaFree(h->wts);
+#endif
+  for (pinn_workspace& w : h->ws) ws_free(w);
+  cudaFree(h->theta_dev); cudaFree(h->stage_dev);
   cudaFreeHost(h->out_pinned); cudaFreeHost(h->theta_pinned);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -113,6 +196,10 @@ int pinn_set_engine(pinn_handle* h, int engine) {
   if (!h) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (engine != PINN_ENGINE_FFMA && engine != PINN_ENGINE_TCGEN05) return fail(h, PINN_EINVAL, "pinn_set_engine: unknown engine");
+#ifndef PINN_AB_BUILD
+  if (engine != PINN_ENGINE_TCGEN05)
+    return fail(h, PINN_ENOTSUP, "pinn_set_engine: this library carries the tcgen05 engine only (the FFMA engine exists in A/B builds, tools/build_ab.sh)");
+#endif
   h->engine = engine;
   return 0;
 }
@@ -266,39 +353,47 @@ static int variant_coef(int variant, VariantCoef* vc, int* nev) {
 }
 
 static int grid_for(pinn_handle* h, long long n) {
-  // both engines give a persistent CTA 4 groups x 32 points per round
-  const long long tiles = (n + 31) / 32;
-  const long long want = (tiles + step_groups() - 1) / step_groups();
+  // one persistent CTA per SM; a CTA works on super-tiles of 128 points
+  const long long want = (n + 127) / 128;
   return (int)(want < h->sm_count ? (want < 1 ? 1 : want) : h->sm_count);
 }
 
-// The FFMA engine reads a weight image prepared by a small kernel; the tcgen05 engine builds its own from p.theta.
+// The step kernel builds its operand images from p.theta itself (A/B builds: the FFMA engine reads an image prepared by
+// a small kernel).
 static int enqueue_prep(pinn_handle* h, const float* theta, StepParams& p, cudaStream_t st) {
   p.theta = theta;
+#ifdef PINN_AB_BUILD
   p.wts = h->wts;
   if (h->engine == PINN_ENGINE_TCGEN05) return 0;
   CU(h, launch_prep(theta, h->wts, st));
   h->launches++;
+#else
+  (void)st;
+#endif
   return 0;
 }
 
 static cudaError_t launch_step_any(pinn_handle* h, int nev, bool train, const StepParams& p, int grid, cudaStream_t st) {
-  return h->engine == PINN_ENGINE_TCGEN05 ? launch_step_tc(nev, train, p, grid, st) : launch_step(nev, train, p, grid, st);
+#ifdef PINN_AB_BUILD
+  if (h->engine != PINN_ENGINE_TCGEN05) return launch_step(nev, train, p, grid, st);
+#endif
+  (void)h;
+  return launch_step_tc(nev, train, p, grid, st);
 }
 
 // Enqueue the fused step kernel for points [first, first + cnt) of a batch; its per-CTA rows go to partial rows
 // [row0, row0 + *rows).  The handle mutex is held by the caller.
-static int enqueue_step_chunk(pinn_handle* h, int nev, StepParams p, int64_t first, int64_t cnt, int row0, int* rows,
-                              cudaStream_t st) {
+static int enqueue_step_chunk(pinn_handle* h, pinn_workspace* ws, int nev, StepParams p, int64_t first, int64_t cnt, int row0,
+                              int* rows, cudaStream_t st) {
   const size_t es = p.in_f64 ? 8 : 4;
   p.x = (const char*)p.x + first * es; p.y = (const char*)p.y + first * es;
   p.z = (const char*)p.z + first * es; p.R = (const char*)p.R + first * es;
   if (p.mask) p.mask += first;
   if (p.E_out) p.E_out += first;
   p.n = cnt;
-  p.partials = h->partials + (size_t)row0 * NPART;
+  p.partials = ws->partials + (size_t)row0 * NPART;
   const int grid = grid_for(h, cnt);
-  if (row0 + grid > h->max_rows) return fail(h, PINN_EINVAL, "internal: partial-row workspace exceeded");
+  if (row0 + grid > ws->rows) return fail(h, PINN_EINVAL, "internal: partial-row workspace exceeded");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) {
     while (h->ev_pool.size() < h->ev_used + 2) {
@@ -335,8 +430,11 @@ int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, con
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
   DevGuard dev_guard(h->device);
-  p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
-  p.bcut = bcutoff; p.partials = h->partials; p.E_out = E_out;
+  pinn_workspace* ws = ws_for(h, st, h->sm_count);
+  if (!ws) return PINN_EINVAL;
+  if (int rc = dp_serialize(h, st)) return rc;
+  p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.n = n; p.in_f64 = in_dtype == PINN_F64;
+  p.bcut = bcutoff; p.partials = ws->partials; p.E_out = E_out;
   p.base_grads = (grad_mask & 0x003Fu) != 0;
   p.gate_grads = (grad_mask & 0xF000u) != 0;
   if (theta_inline) {
@@ -345,16 +443,16 @@ int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, con
   } else {
     if (int rc = enqueue_prep(h, theta, p, st)) return rc;
     if (!weights) {
-      CU(h, launch_count(p, h->counts, h->weights_dev, st));
+      CU(h, launch_count(p, ws->counts, ws->weights, st));
       h->launches += 2;
-      weights = h->weights_dev;
+      weights = ws->weights;
     }
   }
   p.weights = weights;
   int grid = 0;
-  int rc = enqueue_step_chunk(h, nev, p, 0, n, 0, &grid, st);
+  int rc = enqueue_step_chunk(h, ws, nev, p, 0, n, 0, &grid, st);
   if (rc) return rc;
-  CU(h, launch_reduce(h->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
+  CU(h, launch_reduce(ws->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
                       h->dp_on ? h->dp : DpArgs(), st, adam, adam_ticket, presample));
   h->launches++;
   return 0;
@@ -384,7 +482,7 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const voi
   if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_fields: bad in_dtype");
   DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  p.x = x; p.y = y; p.z = z; p.R = R; p.wts = h->wts; p.n = n; p.in_f64 = in_dtype == PINN_F64;
+  p.x = x; p.y = y; p.z = z; p.R = R; p.n = n; p.in_f64 = in_dtype == PINN_F64;
   p.psi = psi; p.lap = lap; p.hpsi = hpsi; p.res = res; p.E_out = E;
   if (int rc = enqueue_prep(h, theta, p, st)) return rc;
   CU(h, launch_step_any(h, nev, false, p, grid_for(h, n), st));
@@ -490,7 +588,10 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     StepParams p{};
     int nev = 0;
     if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_host: unknown variant");
-    p.x = base; p.y = base + col; p.z = base + 2 * col; p.R = base + 3 * col; p.mask = mdev; p.wts = h->wts;
+    pinn_workspace* ws = ws_for(h, st, 4 * h->sm_count);
+    if (!ws) return PINN_EINVAL;
+    if (int rc = dp_serialize(h, st)) return rc;
+    p.x = base; p.y = base + col; p.z = base + 2 * col; p.R = base + 3 * col; p.mask = mdev;
     p.in_f64 = in_dtype == PINN_F64; p.bcut = bcutoff; p.E_out = edev; p.weights = wdev;
     p.base_grads = (grad_mask & 0x003Fu) != 0;
     p.gate_grads = (grad_mask & 0xF000u) != 0;
@@ -500,11 +601,11 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     for (int c = 0; c < nchunk; c++) {
       CU(h, cudaStreamWaitEvent(st, h->ev_chunk[c], 0));
       int r = 0;
-      int rc = enqueue_step_chunk(h, nev, p, first[c], cnt[c], rows, &r, st);
+      int rc = enqueue_step_chunk(h, ws, nev, p, first[c], cnt[c], rows, &r, st);
       if (rc) return rc;
       rows += r;
     }
-    CU(h, launch_reduce(h->partials, rows, wdev, w_inl, grad_mask, outp + 8, outp, edev, n, h->dp_on ? h->dp : DpArgs(), st));
+    CU(h, launch_reduce(ws->partials, rows, wdev, w_inl, grad_mask, outp + 8, outp, edev, n, h->dp_on ? h->dp : DpArgs(), st));
     h->launches++;
   }
   if (E_out_host) CU(h, cudaMemcpyAsync(E_out_host, edev, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

@@ -11,17 +11,29 @@
 
 using namespace pinn;
 
+// Scratch memory of the calls ENQUEUED ON ONE STREAM.  Kernels of one stream run in order, so they may share it; calls
+// that arrive on different streams (torch's current stream, the *_host entry's private stream, every trainer's own
+// stream) may overlap on the device and therefore get one workspace each (ws_for, pinn_capi.cu).
+struct pinn_workspace {
+  cudaStream_t stream = nullptr;
+  double* partials = nullptr;       // [rows][NPART] per-CTA rows of the step kernel
+  int rows = 0;
+  double* weights = nullptr;        // 4 doubles: the output of the set-count kernels when the caller passes no loss weights
+  unsigned long long* counts = nullptr;  // [0..1] boundary-set sizes, [2] batch index of pinn_sample, [3] its block ticket
+  double* grid_partials = nullptr;  // [sm_count + 1][8] dense-grid quadrature rows
+  uint64_t last_use = 0;
+};
+
 struct pinn_handle {
   int device = 0;
   int sm_count = 0;
-  Wts* wts = nullptr;              // prepared weight image
+  std::vector<pinn_workspace> ws;  // one per stream that has called in (guarded by mu)
+  uint64_t ws_clock = 0;
+#ifdef PINN_AB_BUILD
+  Wts* wts = nullptr;              // FFMA engine (A/B builds only): prepared weight image
+#endif
   float* theta_dev = nullptr;      // upload block of the *_host entry: 1536 float ...
-  double* weights_dev = nullptr;   // ... followed by the 3 loss weights (also the output of the set-count kernels)
-  unsigned long long* counts = nullptr;
-  double* partials = nullptr;      // [max_rows][NPART]
-  int max_rows = 0;
-  double* grid_partials = nullptr;  // [sm_count + 1][8] dense-grid quadrature rows
-  unsigned long long* batch_counter = nullptr;  // device counter used by the stand-alone pinn_sample entry
+  double* weights_dev = nullptr;   // ... followed by the 3 loss weights
   // *_host entry
   void* stage_dev = nullptr;       // coordinates + mask
   size_t stage_bytes = 0;
@@ -36,12 +48,16 @@ struct pinn_handle {
   unsigned char* dp_buf = nullptr;
   DpArgs dp;
   bool dp_on = false;
+  cudaStream_t dp_stream = nullptr;  // the exchange buffers carry ONE sequence of steps: the stream of the last exchanging call
+  bool dp_stream_set = false;
   bool dp_opened[DP_MAX_WORLD] = {false, false, false, false, false, false, false, false};  // peer[r] came from cudaIpcOpenMemHandle
   double host_us[4] = {0, 0, 0, 0};   // last pinn_loss_fwd_bwd_host call: submit, wait, copy-out, total (microseconds)
   int64_t launches = 0;
-  int engine = PINN_ENGINE_TCGEN05;  // which implementation of the fused step kernel runs
-  bool host_inline_params = true;     // *_host entry: theta + loss weights inside the kernel parameters (PINN_B200_HOST_INLINE=0: upload)
-  bool host_zero_copy = true;         // pinn_loss_fwd_bwd_host reads page-locked inputs in place (PINN_B200_HOST_ZEROCOPY=0: stage)
+  // The product library has ONE engine (tcgen05) and no run-time knobs.  -DPINN_AB_BUILD (tools/build_ab.sh) adds the
+  // FFMA engine and two environment switches of the *_host entry for A/B measurements.
+  int engine = PINN_ENGINE_TCGEN05;
+  bool host_inline_params = true;     // *_host entry: theta + loss weights inside the kernel parameters
+  bool host_zero_copy = true;         // pinn_loss_fwd_bwd_host reads page-locked inputs in place
   bool profiling = false;          // pinn_profile_begin/collect: CUDA events around the fused step kernel
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -74,6 +90,10 @@ int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, con
                       const double* weights_inline, uint32_t grad_mask, float bcutoff, double* sums, double* dtheta,
                       float* E_out, cudaStream_t st, const pinn::AdamParams* adam = nullptr,
                       unsigned long long* adam_ticket = nullptr, const pinn::SampleParams* presample = nullptr);
+
+// The workspace of stream `st` with room for at least `rows` partial rows (created / grown on first use; the handle mutex
+// is held by the caller).  NULL + error message on failure.
+pinn_workspace* ws_for(pinn_handle* h, cudaStream_t st, int rows);
 
 extern std::string g_create_err;
 

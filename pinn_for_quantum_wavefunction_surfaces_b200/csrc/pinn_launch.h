@@ -22,8 +22,8 @@ struct GridDesc {
 struct StepParams {
   const void *x, *y, *z, *R;
   const uint8_t* mask;
-  const Wts* wts;         // FFMA engine: weight image built by prep_weights_kernel
-  const float* theta;     // tcgen05 engine: the raw parameter vector; every CTA builds its own image in shared memory
+  const Wts* wts;         // A/B builds, FFMA engine: weight image built by prep_weights_kernel
+  const float* theta;     // the raw parameter vector; every CTA builds its own operand images in shared memory
   const double* weights;  // {w_pde, w_bc1, w_bc2}
   double* partials;       // [gridDim.x][NPART]
   float* E_out;
@@ -63,12 +63,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+#ifdef PINN_AB_BUILD  // FFMA engine (pinn_step_ffma.cu), A/B builds only
 cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
-int step_groups();
+cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st);
+#endif
 // tcgen05 engine (pinn_step_tc.cu): super-tiles of 128 points, one persistent CTA per SM
 cudaError_t launch_step_tc(int nev, bool train, const StepParams& p, int grid, cudaStream_t st);
 cudaError_t launch_grid_finish(const double* partials, int nrows, double* out, cudaStream_t st);
-cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st);
 cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st);
 // Data-parallel exchange fused into the reduction kernel: every rank owns one exchange buffer that all
 // peers of the box can write through NVLink peer memory (cudaIpc / peer access).

@@ -1,7 +1,7 @@
-// Fused PINN residual-and-gradient kernels for B200 (sm_100a): the FFMA engine of the step kernel (the first correct
-// path, kept behind pinn_set_engine for A/B measurement against pinn_step_tc.cu) and the small kernels both engines
-// share - set counting, and the reduction of the per-CTA rows, which is also the data-parallel exchange, the optimizer
-// step and the sampler of the device-resident trainer.
+// FFMA engine of the fused step kernel: the first correct path (round 1, v1/v2 in DESIGN.md section 3), kept as the A/B
+// baseline that justifies running the skinny mat-vecs on the tensor cores.  NOT part of the product library: the file
+// is empty unless compiled with -DPINN_AB_BUILD (tools/build_ab.sh builds a separate libpinn_b200_ab.so for
+// bench.py --library ...); the product has one engine and no run-time dispatch.
 //
 // What is computed (closed form of the reference's autograd path, oracle/closed_form.py):
 //   psi, lap psi, residual, loss sums and dLtot/dtheta of the parametric H2+ model
@@ -22,8 +22,8 @@
 //     accumulators persistent in registers over all tiles of the launch.
 //   * bias/vector gradients and the loss sums are reduced over the 32 points of a tile by column sums over
 //     the swizzled shared-memory stash (colsum).
-//   * per-CTA results go to a partial row in global memory; a second tiny kernel adds the rows
-//     in double precision in a fixed order (deterministic).
+//   * per-CTA results go to a partial row in global memory (pinn_reduce.cu adds the rows).
+#ifdef PINN_AB_BUILD
 #include "pinn_device.cuh"
 #include "pinn_sample.cuh"
 #include "pinn_train.h"
@@ -655,234 +655,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ th, Wts* __restric
   build_weight_image<true>(th, out, threadIdx.x, blockDim.x);
 }
 
-// counts of the two boundary sets -> weights {1/n, 1/cnt1, 1/cnt2} (only when the caller passes no weights)
-__global__ void count_sets_kernel(const StepParams p, unsigned long long* counts) {
-  unsigned c1 = 0, c2 = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    if (p.mask) {
-      const unsigned mk = p.mask[i];
-      c1 += mk & 1u; c2 += (mk >> 1) & 1u;
-    } else {
-      const Geom g = load_geom(p, i);
-      c1 += (g.ir1 * p.bcut <= 1.0f); c2 += (g.ir2 * p.bcut <= 1.0f);
-    }
-  }
-  c1 = __reduce_add_sync(0xffffffffu, c1);
-  c2 = __reduce_add_sync(0xffffffffu, c2);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&counts[0], c1); atomicAdd(&counts[1], c2); }
-}
-__global__ void weights_from_counts_kernel(const unsigned long long* counts, long long n, double* w) {
-  w[0] = 1.0 / (double)n;
-  w[1] = 1.0 / (double)counts[0];  // empty set -> inf -> NaN loss, like the reference's mean over an empty selection
-  w[2] = 1.0 / (double)counts[1];
-}
-
-// ---------------------------------------------------------------------------------------------
-// add the partial rows (fixed order, double) -> dtheta, sums
-// block = 1024 threads = 32 entries x 32 row-slices (every thread has at most 5 independent loads in flight: one
-// round trip to L2 instead of a chain of 19)
-//
-// With dp.world > 1 the kernel is also the data-parallel all-reduce, in the style of a low-latency (LL) protocol: every
-// float64 travels as two 8-byte words {32 data bits, 32-bit step number}; 8-byte stores are single-copy atomic, so a
-// reader that sees the step number of this exchange in both words has the value - no fence, no separate flag, one
-// NVLink one-way latency.  Thread (r, e) of block b stores the block's reduced entry e into slot `rank` of peer r's
-// exchange buffer and then polls slot r of its own buffer; the `world` values are added in rank order, so every rank
-// computes bit-identical sums.  No NCCL launch, no extra kernel.  Two slots alternate by step parity: a peer can be at
-// most one exchange ahead (it needs this rank's next contribution to go further).
-// ---------------------------------------------------------------------------------------------
-constexpr int RED_SLICES = 32;
-static_assert(RED_SLICES >= DP_MAX_WORLD, "one row-slice of threads per data-parallel peer");
-struct RedWeights {  // loss weights by value (the *_host entry) instead of through device memory
-  double w[3];
-  int use;
-};
-// Optimizer step fused behind the reduction (the device-resident trainer): every block updates the 32 parameters whose
-// gradient it has just completed; the block that finishes last does the once-per-step bookkeeping.
-struct AdamFuse {
-  int on;
-  AdamParams a;
-  unsigned long long* ticket;  // device, zero between launches
-};
-// The batch of the NEXT step drawn by extra blocks of this launch (blocks DP_BLOCKS .. gridDim.x-1), into the trainer's
-// other batch buffer: the sampler overlaps the reduction / optimizer step instead of standing between two kernels.
-struct SampleFuse {
-  int on;
-  SampleParams s;
-};
-constexpr int PRESAMPLE_BLOCKS = 96;
-__global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const double* __restrict__ partials, int nrows,
-                                                              const double* __restrict__ weights, const RedWeights wi,
-                                                              uint32_t grad_mask,
-                                                              double* __restrict__ dtheta, double* __restrict__ sums,
-                                                              const float* __restrict__ E_out, long long n, const DpArgs dp,
-                                                              const AdamFuse ad, const SampleFuse sf) {
-  if (blockIdx.x >= DP_BLOCKS) {
-    // sampler blocks: they touch nothing the step kernel in front reads or writes (other batch buffer), so they do not
-    // wait for it; the reduction blocks below do, which also keeps this grid from completing early
-    if (sf.on) sample_block(sf.s, blockIdx.x - DP_BLOCKS, gridDim.x - DP_BLOCKS);
-    return;
-  }
-  __shared__ double sh[RED_SLICES][33];
-  __shared__ double tot[32];
-  __shared__ double l3[3];
-  __shared__ int flag_s;
-  const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int idx = blockIdx.x * 32 + e;
-  // launched as a programmatic dependent of the step kernel (which signals launch_dependents when its tile loop is
-  // done): this grid is set up while the step kernel folds its accumulators; the partial rows are complete and
-  // visible once the wait returns
-  pdl_wait();
-  double s = 0.0;
-#pragma unroll 5
-  for (int r = sl; r < nrows; r += RED_SLICES) s += partials[(size_t)r * NPART + idx];
-  sh[sl][e] = s;
-  __syncthreads();
-  unsigned int step = 0;
-  size_t slot = 0;
-  if (dp.world > 1) {
-    unsigned char* own = dp.peer[dp.rank];
-    unsigned long long* ctl = reinterpret_cast<unsigned long long*>(own + DP_ROWS_BYTES);
-    const unsigned long long step64 = ld_acquire_sys(&ctl[0]) + 1;  // ctl[0] = exchanges completed on this rank
-    step = (unsigned int)step64;
-    slot = (size_t)(step64 & 1ull) * DP_MAX_WORLD;
-    if (sl == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int i = 0; i < RED_SLICES; i++) t += sh[i][e];
-      tot[e] = t;
-    }
-    __syncthreads();
-    double v = 0.0;
-    if (sl < dp.world) {
-      const int r = sl;
-      if (r == dp.rank) {
-        v = tot[e];
-      } else {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[e]);
-        unsigned int* dst = reinterpret_cast<unsigned int*>(dp.peer[r]) + ((slot + dp.rank) * NPART + idx) * 4;
-        st_relaxed_sys_v2(dst, (unsigned int)bits, step);
-        st_relaxed_sys_v2(dst + 2, (unsigned int)(bits >> 32), step);
-        const unsigned int* src = reinterpret_cast<const unsigned int*>(own) + ((slot + r) * NPART + idx) * 4;
-        const long long t0 = clock64();
-        uint2 lo, hi;
-        for (;;) {
-          lo = ld_relaxed_sys_v2(src);
-          hi = ld_relaxed_sys_v2(src + 2);
-          if (lo.y == step && hi.y == step) break;
-          if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never arrived; report instead of hanging the GPU
-            ctl[2] = 1ull;
-            break;
-          }
-        }
-        v = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
-      }
-    }
-    __syncthreads();  // every thread is done with sh / tot of the local pass
-    sh[sl][e] = v;    // slices >= world contribute 0; the fixed-order sum below is the sum over ranks
-    __syncthreads();
-    if (threadIdx.x == 0) {  // the last block of the launch closes the exchange (the next launch is stream-ordered behind it)
-      __threadfence();
-      if (atomicAdd(&ctl[1], 1ull) == (unsigned long long)DP_BLOCKS - 1) {
-        ctl[1] = 0ull;
-        st_release_sys(&ctl[0], step64);
-      }
-    }
-  }
-  if (sl == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < RED_SLICES; i++) t += sh[i][e];
-    tot[e] = t;
-    if (idx < NTHETA) {
-      // tensor index of this scalar -> honour grad_mask
-      const int offs[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
-                            O_WGL, O_BGL, O_WG, O_BG, NTHETA};
-      int ti = 0;
-#pragma unroll
-      for (int k = 1; k < 16; k++) ti += (idx >= offs[k]);
-      dtheta[idx] = ((grad_mask >> ti) & 1u) ? t : 0.0;
-    }
-  }
-  __syncthreads();
-  const double w0 = wi.use ? wi.w[0] : weights[0], w1 = wi.use ? wi.w[1] : weights[1], w2 = wi.use ? wi.w[2] : weights[2];
-  constexpr int SB = S_RES2 / 32, b = S_RES2 - SB * 32;   // the block / lane that own the loss sums
-  if (blockIdx.x == SB && threadIdx.x == 0) {
-    const double r2 = tot[b], p1 = tot[b + 1], p2 = tot[b + 2], sE = tot[b + 3];
-    const double Lpde = w0 * r2, Lbc = w1 * p1 + w2 * p2;
-    sums[0] = Lpde + Lbc; sums[1] = Lpde; sums[2] = Lbc; sums[3] = sE;
-    sums[4] = r2; sums[5] = p1; sums[6] = p2;
-    sums[7] = (E_out && n > 0) ? (double)E_out[n - 1] : 0.0;
-  }
-  if (!ad.on) return;
-
-  // ---- fused optimizer step.  Every block needs Ltot for the best-model rule: the blocks that do not own the loss
-  //      sums add those three entries themselves, in exactly the order used above (row slices, then slices in order,
-  //      then ranks in order), so that all blocks - and all ranks - decide on identical bits ----
-  if (blockIdx.x == SB) {
-    if (threadIdx.x < 3) l3[threadIdx.x] = tot[b + threadIdx.x];
-  } else {
-    if (threadIdx.x < 96) {
-      const int j = threadIdx.x >> 5, sj = threadIdx.x & 31;
-      double ps = 0.0;
-#pragma unroll 5
-      for (int r = sj; r < nrows; r += RED_SLICES) ps += partials[(size_t)r * NPART + S_RES2 + j];
-      sh[sj][j] = ps;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      const int j = threadIdx.x;
-      double local = 0.0;
-#pragma unroll
-      for (int i = 0; i < RED_SLICES; i++) local += sh[i][j];
-      double g = local;
-      if (dp.world > 1) {
-        const unsigned char* own = dp.peer[dp.rank];
-        g = 0.0;
-        for (int r = 0; r < dp.world; r++) {
-          double v = local;
-          if (r != dp.rank) {  // the peer's block SB deposits this entry in our buffer; only read here
-            const unsigned int* src = reinterpret_cast<const unsigned int*>(own) + ((slot + r) * NPART + S_RES2 + j) * 4;
-            const long long t0 = clock64();
-            uint2 lo, hi;
-            for (;;) {
-              lo = ld_relaxed_sys_v2(src);
-              hi = ld_relaxed_sys_v2(src + 2);
-              if ((lo.y == step && hi.y == step) || clock64() - t0 > 6000000000ll) break;
-            }
-            v = __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
-          }
-          g += v;
-        }
-      }
-      l3[j] = g;
-    }
-  }
-  __syncthreads();
-  const AdamParams& a = ad.a;
-  const unsigned long long tstep = *a.step;  // read before any block can finish the step (the last block advances it)
-  const double Lpde = w0 * l3[0], Lbc = w1 * l3[1] + w2 * l3[2];
-  const double Ltot = Lpde + Lbc;
-  const bool take_best = adam_take_best(a, tstep, Ltot);
-  if (sl == 0 && idx < NTHETA) adam_update_entry(a, adam_coef(a, tstep), idx, tot[e], take_best);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    flag_s = atomicAdd(ad.ticket, 1ull) == (unsigned long long)DP_BLOCKS - 1;
-    if (flag_s) {  // every block has updated its parameters and read the step / best loss; the loss sums are visible
-      __threadfence();
-      const double sv[8] = {ld_acquire_gpu(&sums[0]), ld_acquire_gpu(&sums[1]), ld_acquire_gpu(&sums[2]), ld_acquire_gpu(&sums[3]),
-                            0.0, 0.0, 0.0, ld_acquire_gpu(&sums[7])};
-      adam_bookkeeping(a, tstep, sv, take_best);
-      *ad.ticket = 0ull;
-    }
-  }
-}
-
 }  // namespace pinn
 
-// =================================================================================================
-// host-side launchers used by pinn_capi.cu
-// =================================================================================================
 namespace pinn {
 
 template <int NEV, int G, bool TRAIN>
@@ -907,33 +681,11 @@ cudaError_t launch_step(int nev, bool train, const StepParams& p, int grid, cuda
   if (nev == 2) return train ? launch_step_t<2, GROUPS, true>(p, grid, st) : launch_step_t<2, GROUPS, false>(p, grid, st);
   return train ? launch_step_t<1, GROUPS, true>(p, grid, st) : launch_step_t<1, GROUPS, false>(p, grid, st);
 }
-int step_groups() { return GROUPS; }
 
 cudaError_t launch_prep(const float* theta, Wts* out, cudaStream_t st) {
   prep_weights_kernel<<<1, 256, 0, st>>>(theta, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double* weights, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return e;
-  count_sets_kernel<<<296, 256, 0, st>>>(p, counts);
-  weights_from_counts_kernel<<<1, 1, 0, st>>>(counts, p.n, weights);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
-                          uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
-                          cudaStream_t st, const AdamParams* adam, unsigned long long* adam_ticket,
-                          const SampleParams* presample) {
-  AdamFuse ad{};
-  if (adam) { ad.on = 1; ad.a = *adam; ad.ticket = adam_ticket; }
-  SampleFuse sf{};
-  if (presample) { sf.on = 1; sf.s = *presample; }
-  RedWeights wi{};
-  if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
-  return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS + (presample ? PRESAMPLE_BLOCKS : 0)), dim3(RED_SLICES * 32), 0, st,
-                    partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp, ad, sf);
-}
-
 }  // namespace pinn
+#endif  // PINN_AB_BUILD

@@ -38,6 +38,8 @@ struct AdamParams {
   double lr, beta1, beta2, eps, best_after;
   uint32_t grad_mask;
   int best_mode, hist_mean_E;
+  unsigned long long step_base;  // optimizer steps done when this run (re)started: history rows and train.py's
+                                 // "take the first loss" rule count from here (pinn_trainer_load_state)
 };
 
 // One kernel.  zero_counts: put a memset of the two counters in front (callers that own `counts`; the trainer keeps them
@@ -80,14 +82,14 @@ __device__ inline void adam_update_entry(const AdamParams& a, const AdamCoef& c,
   a.theta32[i] = (float)th;
 }
 __device__ inline bool adam_take_best(const AdamParams& a, unsigned long long t, double Ltot) {
-  if (a.best_mode == 0) return (t == 0ull) || (Ltot < *a.best_loss);              // train.py:58
+  if (a.best_mode == 0) return (t == a.step_base) || (Ltot < *a.best_loss);       // train.py:58
   return ((double)t > a.best_after) && (Ltot < *a.best_loss);                     // poc/main.py:414 (Llim starts at 10)
 }
 // once per step, after every entry was updated: history row, best-loss record, step counter
 __device__ inline void adam_bookkeeping(const AdamParams& a, unsigned long long t, const double* sums, bool take_best) {
   const double Ltot = sums[0];
-  if (a.hist && (long long)t < a.hist_cap) {
-    double* h = a.hist + 4 * t;
+  if (a.hist && (long long)(t - a.step_base) < a.hist_cap) {
+    double* h = a.hist + 4 * (t - a.step_base);
     h[0] = Ltot; h[1] = sums[1]; h[2] = sums[2];
     h[3] = a.hist_mean_E ? sums[3] / (double)a.n : sums[7];  // train.py prints mean(e); poc keeps E[-1]
   }

@@ -31,6 +31,7 @@ struct pinn_trainer {
   cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [cur][draw the next batch too]
   bool warmed = false;  // one plain step has run: one-time kernel attributes are set outside any capture
   int64_t steps_issued = 0;
+  int64_t step_base = 0;  // optimizer steps done when the run (re)started (pinn_trainer_load_state)
   bool have_batch = false;
 };
 
@@ -69,6 +70,7 @@ static int trainer_enqueue(pinn_trainer* t, bool sample_now, bool presample_next
   a.n = c.n * ((h->dp_on && h->dp.world > 1) ? h->dp.world : 1);  // mean E of the history is over the global batch
   a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.eps; a.best_after = (double)c.best_after;
   a.grad_mask = c.grad_mask; a.best_mode = c.best_mode; a.hist_mean_E = c.history_mean_E;
+  a.step_base = (unsigned long long)t->step_base;
   SampleParams next{};
   if (presample_next) next = sampler_params(t, b ^ 1);
   // the optimizer step (and the next batch) ride in the reduction kernel: two launches per step
@@ -105,14 +107,17 @@ int pinn_sample(pinn_handle* h, int64_t n, uint64_t seed, uint64_t batch, const 
     return fail(h, PINN_EINVAL, "pinn_sample: bad argument");
   DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  set_u64_kernel<<<1, 1, 0, st>>>(h->batch_counter, (unsigned long long)batch);
+  pinn_workspace* ws = ws_for(h, st, h->sm_count);
+  if (!ws) return PINN_EINVAL;
+  unsigned long long* batch_counter = ws->counts + 2;  // [2] batch index, [3] block ticket of the sampler
+  set_u64_kernel<<<1, 1, 0, st>>>(batch_counter, (unsigned long long)batch);
   SampleParams s{};
-  s.n = n; s.seed = seed; s.batch_counter = h->batch_counter;
+  s.n = n; s.seed = seed; s.batch_counter = batch_counter;
   s.xL = box[0]; s.xR = box[1]; s.yL = box[2]; s.yR = box[3]; s.zL = box[4]; s.zR = box[5]; s.RL = box[6]; s.RR = box[7];
   s.cutoff = cutoff; s.bcutoff = bcutoff;
   s.x = x; s.y = y; s.z = z; s.R = R; s.mask = mask; s.counts = (unsigned long long*)counts;
   s.index_offset = 0;
-  s.weights = weights; s.ticket = h->batch_counter + 1; s.reset_counts = 0;
+  s.weights = weights; s.ticket = batch_counter + 1; s.reset_counts = 0;
   CU(h, launch_sample(s, true, st));
   h->launches += 2;
   return 0;
@@ -161,17 +166,19 @@ int pinn_grid_reduce(pinn_handle* h, int variant, const float* theta, int nx, in
   else return fail(h, PINN_EINVAL, "pinn_grid_reduce: unknown variant");
   DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  pinn_workspace* ws = ws_for(h, st, h->sm_count);
+  if (!ws) return PINN_EINVAL;
   p.n = (long long)nx * ny * nz;
   p.theta = theta;
   p.grid.on = 1; p.grid.nx = nx; p.grid.ny = ny; p.grid.nz = nz;
   p.grid.x0 = lim[0]; p.grid.dx = (lim[1] - lim[0]) / (nx - 1);
   p.grid.y0 = lim[2]; p.grid.dy = (lim[3] - lim[2]) / (ny - 1);
   p.grid.z0 = lim[4]; p.grid.dz = (lim[5] - lim[4]) / (nz - 1);
-  p.grid.R = R; p.grid.wx = wx; p.grid.wy = wy; p.grid.wz = wz; p.grid.partials = h->grid_partials;
+  p.grid.R = R; p.grid.wx = wx; p.grid.wy = wy; p.grid.wz = wz; p.grid.partials = ws->grid_partials;
   const long long tiles = (p.n + 127) / 128;
   const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
   CU(h, launch_step_tc(nev, false, p, grid, st));  // the dense-grid mode lives in the tcgen05 kernel
-  CU(h, launch_grid_finish(h->grid_partials, grid, out, st));
+  CU(h, launch_grid_finish(ws->grid_partials, grid, out, st));
   h->launches += 2;
   return 0;
 }
@@ -268,7 +275,20 @@ int pinn_trainer_load_state(pinn_trainer* t, const double* theta, const double* 
   if (v) CU(h, cudaMemcpy(t->v, v, NTHETA * 8, cudaMemcpyHostToDevice)); else CU(h, cudaMemset(t->v, 0, NPART * 8));
   const unsigned long long s = (unsigned long long)step;
   CU(h, cudaMemcpy(t->step, &s, 8, cudaMemcpyHostToDevice));
+  // a resumed run starts its own best-model record and history: the loaded parameters are the best known so far, the
+  // loss limit is back at its initial value, history row 0 is the first step after the resume
+  CU(h, cudaMemcpy(t->best_theta, theta, NTHETA * 8, cudaMemcpyHostToDevice));
+  const double llim = 10.0;
+  const long long neg1 = -1;
+  CU(h, cudaMemcpy(t->best_loss, &llim, 8, cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(t->best_step, &neg1, 8, cudaMemcpyHostToDevice));
+  if (t->hist) CU(h, cudaMemset(t->hist, 0, (size_t)t->cfg.history_capacity * 4 * 8));
   t->steps_issued = step;
+  t->step_base = step;
+  // captured graphs carry the old step_base in their kernel parameters
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++)
+      if (t->graph[a][b]) { cudaGraphExecDestroy(t->graph[a][b]); t->graph[a][b] = nullptr; }
   return 0;
 }
 
@@ -361,6 +381,13 @@ int pinn_trainer_read(pinn_trainer* t, double* theta, double* m, double* v, doub
   if (history && history_rows > 0) {
     const int64_t rows = history_rows < t->cfg.history_capacity ? history_rows : t->cfg.history_capacity;
     if (rows > 0) CU(h, cudaMemcpy(history, t->hist, (size_t)rows * 4 * 8, cudaMemcpyDeviceToHost));
+  }
+  if (h->dp_on && h->dp.world > 1 && h->dp_buf) {  // a data-parallel run whose exchange failed stopped updating: say so
+    unsigned long long failed = 0;
+    CU(h, cudaMemcpy(&failed, h->dp_buf + DP_ROWS_BYTES + 2 * sizeof(unsigned long long), sizeof(failed), cudaMemcpyDeviceToHost));
+    if (failed)
+      return fail(h, PINN_ETIMEDOUT, "pinn_trainer_read: a data-parallel peer did not deliver its partial sums; the optimizer "
+                                     "steps from the failed exchange on were skipped (values read are those before it)");
   }
   return 0;
 }

@@ -70,3 +70,21 @@ def grad_mask_from_requires_grad(tensors, order="poc"):
         if getattr(t, "requires_grad", False):
             mask |= 1 << (i if order == "poc" else TRAINPY_TO_POC[i])
     return mask
+
+
+def check_supported_model(params=None, model=None):
+    """The kernels implement the model the reference ships and trains: inversion symmetry P = +1 (base(f1,f2) + base(f2,f1)
+    and LCAO f1 + f2, poc/main.py:255-260, 289) with the nuclei on the x axis (Ry = Rz = 0, poc/main.py:28-29, 44).
+    Anything else - `params['inversion_symmetry'] = -1`, displaced nuclei - would silently train on the wrong loss, so
+    it is refused.  `params`: the reference's parameter dict; `model`: an NN_ion instance (its P, Ry, Rz attributes)."""
+    from ._lib import PinnError
+    vals = {}
+    if params is not None:
+        vals.update({"inversion_symmetry": params.get("inversion_symmetry", 1), "Ry": params.get("Ry", 0),
+                     "Rz": params.get("Rz", 0)})
+    if model is not None:
+        vals.update({"inversion_symmetry": getattr(model, "P", vals.get("inversion_symmetry", 1)),
+                     "Ry": getattr(model, "Ry", vals.get("Ry", 0)), "Rz": getattr(model, "Rz", vals.get("Rz", 0))})
+    if vals.get("inversion_symmetry", 1) != 1 or vals.get("Ry", 0) != 0 or vals.get("Rz", 0) != 0:
+        raise PinnError("unsupported model configuration %r: the fused kernels implement inversion_symmetry = +1 with "
+                        "Ry = Rz = 0 (poc/main.py:28-29, 44, 255-260) only" % (vals,))

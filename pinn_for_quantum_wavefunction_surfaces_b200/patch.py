@@ -12,6 +12,7 @@ import io
 import os
 
 from . import ops
+from .params import check_supported_model
 
 _HOT_FIRST = "r1 = torch.sqrt((x - R)**2 + y**2 + z**2)"
 _HOT_LAST = "Ltot = Lpde + Lbc"
@@ -23,6 +24,8 @@ def patch_nn_ion(nn_ion_cls, loss_fn=None):
     fn = loss_fn or ops.loss_poc
 
     def LossFunctions(self, x, y, z, R, params, bIndex1, bIndex2):  # same signature as poc/main.py:341
+        # the kernel hard-codes what the shipped model uses: P = +1, nuclei on the x axis; refuse anything else
+        check_supported_model(params if isinstance(params, dict) else None, self)
         return fn(self, x, y, z, R, bIndex1, bIndex2)
 
     nn_ion_cls.LossFunctions = LossFunctions

@@ -108,12 +108,17 @@ class Trainer:
         rc = self.h.L.pinn_trainer_create(self.h.h, ctypes.byref(c), th.ctypes.data_as(ctypes.c_void_p), ctypes.byref(tp))
         self.h.check(rc, "pinn_trainer_create")
         self.t = tp
+        self._step_base = 0
 
     def load_state(self, theta, m=None, v=None, step=0):
+        """Resume: parameters, Adam moments (None = zeros) and the number of optimizer steps already done.  The resumed run
+        starts its own best-model record (best_theta = the loaded parameters until a step qualifies) and its own history
+        (row 0 = the first step after the resume); `freeze_after`, `best_after` and `sc_sampling` keep counting absolute steps."""
         a = lambda x: None if x is None else np.ascontiguousarray(np.asarray(x, np.float64).ravel())
         th, mm, vv = a(theta), a(m), a(v)
         p = lambda x: None if x is None else x.ctypes.data_as(ctypes.c_void_p)
         self.h.check(self.h.L.pinn_trainer_load_state(self.t, p(th), p(mm), p(vv), step), "pinn_trainer_load_state")
+        self._step_base = int(step)
 
     def set_batch(self, x, y, z, R, mask, weights):
         """Use caller-provided points (CUDA or CPU float32 tensors) until the next resampling step."""
@@ -141,7 +146,7 @@ class Trainer:
         self.h.check(rc, "pinn_trainer_read")
         steps = int(sc[0])
         return {"theta": theta, "m": m, "v": v, "best_theta": best, "steps": steps, "best_loss": float(sc[1]),
-                "best_step": int(sc[2]), "batches": int(sc[3]), "history": hist[:min(rows, steps)]}
+                "best_step": int(sc[2]), "batches": int(sc[3]), "history": hist[:max(0, min(rows, steps - self._step_base))]}
 
     def close(self):
         if self.t:
@@ -168,6 +173,26 @@ def init_trainpy(seed=12345):
         t.uniform_(-lim, lim, generator=g)
         ts.append(t)
     return P.pack_trainpy(ts, dtype=torch.float64).numpy()
+
+
+def init_poc(seed=0):
+    """A freshly constructed NN_ion (poc/main.py:233-245): `nn.Linear` default initialisation in float64, layers created in
+    the reference's order, `Lin_Eout.bias = -1` -> packed theta (float64).  Equals the real class under
+    `torch.manual_seed(seed)` (tests/golden/checkpoints.npz: init_seed0)."""
+    nh, ne, nl = 16, 32, 10
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        dims = [(2, nh), (nh, nh), (nh, 1), (1, ne), (ne, ne), (ne, 1), (1, nl), (nl, 1)]
+        layers = [torch.nn.Linear(i, o, dtype=torch.float64) for i, o in dims]
+    finally:
+        torch.set_rng_state(state)
+    with torch.no_grad():
+        layers[5].bias.fill_(-1.0)
+    ts = []
+    for L in layers:
+        ts += [L.weight, L.bias]
+    return P.pack_poc(ts, dtype=torch.float64).numpy()
 
 
 def train_trainpy(theta0=None, n=10000, epochs=1000, lr=8e-3, seed=12345, fine_tune=False, use_graph=False, log_every=0):
@@ -203,6 +228,7 @@ def train_poc(theta0, params=None, freezeUnits=False, seed=0, use_graph=False):
     pr = {"xL": -18, "xR": 18, "yL": -18, "yR": 18, "zL": -18, "zR": 18, "RxL": 0.2, "RxR": 4, "cutOff": 0.005,
           "BCcutoff": 17.5, "sc_sampling": 1, "n_train": 100000, "epochs": 5000, "lr": 8e-3}
     pr.update(params or {})
+    P.check_supported_model(pr)
     epochs = int(pr["epochs"])
     box = (pr["xL"], pr["xR"], pr["yL"], pr["yR"], pr["zL"], pr["zR"], pr["RxL"], pr["RxR"])
     # resample while tt < 0.9*epochs (main.py:396); save when tt > 0.5*epochs and Ltot < Llim (main.py:414)

@@ -37,6 +37,18 @@ from oracle import layout  # noqa: E402
 warnings.filterwarnings("ignore")
 
 
+class _NumpyOnlyUnpickler(pickle.Unpickler):
+    """poc/energy_R_ion.pkl is a dict of numpy arrays; refuse every other global (untrusted content)."""
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+                ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "scalar"),
+                ("numpy._core.multiarray", "scalar")}
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise pickle.UnpicklingError("refusing to load %s.%s from the reference pickle" % (module, name))
+        return super().find_class(module, name)
+
+
 def load_poc_namespace():
     import torch.nn as nn
     import torch.optim as optim
@@ -63,8 +75,15 @@ def golden_poc():
     out = {}
     thetas = {}
     for tag in ("ionHsym", "ionHsym_fineTune"):
-        ck = torch.load(os.path.join(REF, "models", tag + ".pt"), map_location="cpu")
+        # the reference tree is untrusted content: tensors only, no arbitrary pickles
+        ck = torch.load(os.path.join(REF, "models", tag + ".pt"), map_location="cpu", weights_only=True)
         thetas[tag] = layout.pack_poc([v.numpy() for v in ck["model_state_dict"].values()])
+    # a freshly constructed NN_ion (nn.Linear default init + Lin_Eout.bias = -1, poc/main.py:233-245) under seed 0:
+    # pins init_poc(), the starting point of the device-resident paper-schedule run
+    torch.manual_seed(0)
+    m0 = ns["NN_ion"](params)
+    thetas["init_seed0"] = layout.pack_poc([v.detach().numpy() for v in m0.state_dict().values()])
+    assert [k for k in m0.state_dict()] == [k for k, _ in m0.named_parameters()]   # parameters() order == state_dict order
     np.savez(os.path.join(HERE, "checkpoints.npz"), **thetas)
 
     torch.manual_seed(0)
@@ -94,7 +113,7 @@ def golden_poc():
     np.savez_compressed(os.path.join(HERE, "poc_seed0_n4096.npz"), **out)
 
     with open(os.path.join(REF, "poc", "energy_R_ion.pkl"), "rb") as f:
-        d = pickle.load(f)
+        d = _NumpyOnlyUnpickler(f).load()
     Rex, Eex = ns["exactE"]()
     np.savez(os.path.join(HERE, "energy_R_ion.npz"), R=np.asarray(d["R"]), E_net=np.asarray(d["E_net"]),
              E_int=np.asarray(d["E_int"]), Elcao=np.asarray(d["Elcao"]), R_exact=np.asarray(Rex),
@@ -149,10 +168,15 @@ def golden_trainpy():
                         e=e.detach().numpy().ravel())
     print("train.py hot-line goldens:", Ltot.item(), Lpde.item(), Lbc.item())
 
-    # whole-script trace: BASELINE config 1 shortened (n=4096, epochs=40), otherwise unmodified
+    # whole-script traces: BASELINE config 1 (n=4096, epochs=200) and its first 40 epochs, otherwise unmodified
+    for epochs in (40, 200):
+        whole_script_trace(4096, epochs)
+
+
+def whole_script_trace(n, epochs):
     src = open(os.path.join(REF, "train.py")).read()
-    src = src.replace("n = 10000", "n = 4096").replace("epochs=1000)", "epochs=40)")
-    assert "n = 4096" in src and "epochs=40)" in src
+    src = src.replace("n = 10000", "n = %d" % n).replace("epochs=1000)", "epochs=%d)" % epochs)
+    assert "n = %d" % n in src and "epochs=%d)" % epochs in src
     cwd = os.getcwd()
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
@@ -167,12 +191,17 @@ def golden_trainpy():
             os.chdir(cwd)
     torch.set_default_dtype(torch.double)
     trace = [ln.strip() for ln in buf.getvalue().strip().split("\n")]
-    with open(os.path.join(HERE, "trainpy_trace_n4096_e40.json"), "w") as f:
-        json.dump({"n": 4096, "epochs": 40, "seed": 12345, "trace": trace, "model_bin_md5": md5,
-                   "model_bin_size": len(blob), "torch": torch.__version__}, f, indent=1)
-    with open(os.path.join(HERE, "trainpy_model_n4096_e40.bin"), "wb") as f:
+    tag = "n%d_e%d" % (n, epochs)
+    with open(os.path.join(HERE, "trainpy_trace_%s.json" % tag), "w") as f:
+        json.dump({"n": n, "epochs": epochs, "seed": 12345, "trace": trace, "model_bin_md5": md5,
+                   "model_bin_size": len(blob), "torch": torch.__version__,
+                   # the md5 is bit-level and follows the summation order of torch.mean: 1 / 8 / 16 threads give three
+                   # different files whose parameters agree to 4e-15 after 200 steps (tests compare values, not the md5)
+                   "threads": torch.get_num_threads()}, f, indent=1)
+    with open(os.path.join(HERE, "trainpy_model_%s.bin" % tag), "wb") as f:
         f.write(blob)
     print("\n".join(trace))
+    print("md5(model.bin) =", md5)
 
 
 if __name__ == "__main__":

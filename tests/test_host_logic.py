@@ -137,6 +137,95 @@ def test_patch_nn_ion_signature():
     assert orig(Fake(), 1, 2, 3, 4, None, 5, 6) == "orig"
 
 
+def _oracle_poc_loss(model, x, y, z, R, bIndex1, bIndex2):
+    """Stand-in for ops.loss_poc built on the CPU oracle (tests only): same contract - the model's 16 parameters in
+    parameters() order, torch.where tuples as index sets, gradients only for the tensors with requires_grad."""
+    ps = list(model.parameters())
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *tensors):
+            theta = layout.pack_poc([t.detach().numpy() for t in tensors])
+            n = x.shape[0]
+            m1 = np.zeros(n); m1[bIndex1[0].numpy()] = 1
+            m2 = np.zeros(n); m2[bIndex2[0].numpy()] = 1
+            o = cf.loss_and_grad("poc", theta, *[v.detach().numpy().ravel() for v in (x, y, z, R)], m1, m2)
+            ctx.g = [torch.tensor(a) for a in layout.unpack_poc(o["grad"])]
+            ctx.needs = [t.requires_grad for t in tensors]
+            t = lambda v: torch.tensor(v, dtype=torch.float64)
+            outs = (t(o["Ltot"]), t(o["Lpde"]), t(o["Lbc"]), t(o["E"]).reshape(-1, 1))
+            ctx.mark_non_differentiable(*outs[1:])
+            return outs
+
+        @staticmethod
+        def backward(ctx, g, *_):
+            return tuple((g * a.reshape(a.shape)) if need else None for a, need in zip(ctx.g, ctx.needs))
+    return F.apply(*ps)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "poc", "main.py")), reason="reference not mounted")
+def test_patch_the_real_nn_ion_and_run_the_reference_train(tmp_path, golden_dir):
+    """The drop-in seam on the REAL class: NN_ion is loaded from the reference file (AST, as tests/golden/make_golden.py
+    does), patched with patch_nn_ion, and the reference's own train() (poc/main.py:359-430: sampler, Adam, freeze flags,
+    history arrays, .pt writer) runs on top of it - once unpatched, once patched with the oracle loss, same seed.  Also pins
+    the assumption the packing relies on: parameters() order == state_dict() order == pk.POC_TENSOR_NAMES."""
+    import pickle
+    import time
+    from os import path
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden as mg
+    torch.set_default_dtype(torch.double)
+    try:
+        cwd = os.getcwd()
+        os.chdir(tmp_path)
+        os.makedirs("models"); os.makedirs("data")
+        hist = {}
+        for patched in (False, True):
+            ns = mg.load_poc_namespace()
+            ns.update(path=path, time=time, pickle=pickle)
+            NN_ion = ns["NN_ion"]
+            m = NN_ion(ns["params"])
+            assert [k for k, _ in m.named_parameters()] == list(m.state_dict().keys()) == pk.POC_TENSOR_NAMES
+            if patched:
+                orig = pk.patch_nn_ion(NN_ion, loss_fn=_oracle_poc_loss)
+                assert orig is not None
+            for stage, (epochs, lr, freeze) in enumerate(((6, 8e-3, False), (4, 5e-4, True))):
+                prm = ns["set_params"]()
+                prm.update(epochs=epochs, n_train=1500, lr=lr, lossPath="data/loss_%d.pkl" % stage,
+                           saveModelPath="models/m.pt", loadModelPath="models/m.pt")
+                torch.manual_seed(3 + stage)
+                ns["train"](prm, loadWeights=freeze, freezeUnits=freeze)
+                with open("data/loss_%d.pkl" % stage, "rb") as f:
+                    hist[(patched, stage)] = pickle.load(f)
+            sd = torch.load("models/m.pt", weights_only=True)["model_state_dict"]
+            hist[(patched, "theta")] = layout.pack_poc([v.numpy() for v in sd.values()])
+        for stage in (0, 1):
+            for k in ("Ltot", "Lpde", "Lbc", "Energy"):
+                a, b = hist[(False, stage)][k], hist[(True, stage)][k]
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-14), (stage, k)
+        assert np.abs(hist[(False, "theta")] - hist[(True, "theta")]).max() < 1e-10
+        # the fine-tune stage moved the E-net tensors only (freezeBase + freezeDecayUnit, poc/main.py:305-319)
+        # a model the kernels do not implement is refused instead of silently trained on the wrong loss
+        bad = dict(ns["set_params"](), inversion_symmetry=-1)
+        mb = NN_ion(bad)
+        x, y, z, R = ns["sampling"](bad, 64)
+        with pytest.raises(pk.PinnError):
+            mb.LossFunctions(x, y, z, R, bad, (torch.tensor([0]), torch.tensor([0])), (torch.tensor([1]), torch.tensor([0])))
+    finally:
+        os.chdir(cwd)
+        torch.set_default_dtype(torch.float32)
+
+
+def test_unsupported_model_configurations_are_refused():
+    P.check_supported_model({"inversion_symmetry": 1, "Ry": 0, "Rz": 0})
+    P.check_supported_model(None, None)
+    for bad in ({"inversion_symmetry": -1}, {"Ry": 0.5}, {"Rz": -1}):
+        with pytest.raises(pk.PinnError):
+            P.check_supported_model(bad)
+    with pytest.raises(pk.PinnError):
+        pk.train_poc(np.zeros(1521), {"inversion_symmetry": -1})
+
+
 DP_WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])

@@ -69,15 +69,18 @@ def test_simpson_rules():
     assert abs(sp.integra3d(ax, ax, ax, F) - np.einsum("i,j,k,ijk->", w, w, w, F)) < 1e-12
 
 
-def test_training_loop_restatement_reproduces_the_reference_run(golden_dir):
+@pytest.mark.parametrize("epochs", [40, 200])
+def test_training_loop_restatement_reproduces_the_reference_run(golden_dir, epochs):
     """oracle.train_loop.trainpy_run (train.py:13-110 restated) + the float64 oracle loss == the real script's trace and
-    model.bin (fixtures written by tests/golden/make_golden.py from the unmodified reference)."""
-    tr = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e40.json")))
-    params, trace, hist = tl.trainpy_run(tl.oracle_trainpy_op, n=4096, epochs=40)
+    model.bin (fixtures written by tests/golden/make_golden.py from the unmodified reference).  200 epochs at n = 4096 is
+    BASELINE config 1 as written (train.py:81, 110 with n, epochs replaced)."""
+    tr = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e%d.json" % epochs)))
+    params, trace, hist = tl.trainpy_run(tl.oracle_trainpy_op, n=4096, epochs=epochs)
     assert trace == tr["trace"]
-    ref = pk.convert.read_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e40.bin"))
+    ref = pk.convert.read_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e%d.bin" % epochs))
     for a, b in zip(params, ref):
-        assert a.shape == b.shape and np.abs(a.detach().numpy() - b).max() < 1e-13
+        # (the real script's own result moves by 4e-15 with the thread count of torch.mean over 200 steps)
+        assert a.shape == b.shape and np.abs(a.detach().numpy() - b).max() < 1e-12
     assert len(tl.model_bin_bytes(params)) == tr["model_bin_size"]
 
 
