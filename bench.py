@@ -7,8 +7,11 @@ A step = one training evaluation (forward + Laplacian + loss + parameter gradien
 sum of the 8 + 1521 float64 over the ranks, fused into the reduction kernel or, --allreduce nccl, as a
 separate all-reduce) of the poc-form ionHsym model on one batch of P synthetic collocation points per GPU
 (default 2^18 = BASELINE config 3; weak scaling: every GPU gets its own P points).
-Prints ONE JSON line (rank 0): value (device-resident inputs), roofline (kernel events, ncu figures of the
-committed capture), e2e (page-locked host inputs through HostStep / pinn_loss_fwd_bwd_host), and at N=1
+Prints ONE JSON line (rank 0): value (device-resident inputs), roofline (kernel events; FP32 peak measured in this run;
+ncu figures of the committed capture when it belongs to this build), e2e (page-locked host inputs through HostStep /
+pinn_loss_fwd_bwd_host), seam_e2e (the reference-style loop: patched LossFunctions -> backward -> torch Adam -> .cpu()),
+config4_global_batch (2^22 points/step sharded over the ranks), value_steady (>= 1000 steps), at N>1 dp_parity (the fused
+exchange against one GPU and against an NCCL all-reduce, on a common batch, before anything is timed), and at N=1
 cpu_baseline, reference_autograd_on_gpu, dense_grid_inference, device_train_loop.  See DESIGN.md section 5.
 """
 import argparse
@@ -25,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_POINT = 27044.0          # canonical algorithmic FLOPs of one poc training step
-FP32_PEAK_MEASURED = 72.0e12      # tools/microbench/pipes.cu on this pool's B200: 3.60e13 FFMA/s (profiles/r01_microbench_pipes.jsonl)
+FP32_PEAK_FALLBACK = 72.0e12      # round-1 measurement (profiles/r01_microbench_pipes.jsonl); the run measures its own
 FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9
 N_BATCHES = 40                    # rotating input batches: 40 x 4 MiB = 168 MB > 126 MB L2
 
@@ -84,16 +87,24 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
 
 
-def cpu_reference_points_per_s(theta, min_seconds, max_points=1 << 16, threads=None):
-    """The reference's own way of computing the step (nested autograd, float64, all host threads):
-    oracle/ref_autograd.py.  Bounded sample: `max_points` points per evaluation, repeated >= min_seconds."""
+def host_threads():
+    """All host cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which is why
+    the thread count is set explicitly here instead of being left to the environment."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_points_per_s(theta, min_seconds, points=1 << 18):
+    """The reference's own way of computing the step (nested autograd, float64, all host threads): oracle/ref_autograd.py
+    on one full batch of `points` points, repeated for >= min_seconds."""
     import torch
     from oracle import ref_autograd as ra
-    if threads:
-        torch.set_num_threads(threads)
-    cores = torch.get_num_threads()
+    cores = host_threads()
+    torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1234)
-    x, y, z, R, i1, i2 = ra.sample_box(max_points, "poc", g)
+    x, y, z, R, i1, i2 = ra.sample_box(points, "poc", g)
     th = torch.tensor(theta, dtype=torch.float64)
     ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)  # warm-up
     times = []
@@ -103,7 +114,8 @@ def cpu_reference_points_per_s(theta, min_seconds, max_points=1 << 16, threads=N
         ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
         times.append(time.time() - t0)
     best = min(times)
-    return max_points / best, cores, "%d points x %d evaluations (best of), float64 nested autograd" % (max_points, len(times)), best
+    return points / best, cores, ("%d points (the full batch) x %d evaluations (best of), float64 nested autograd, %d threads"
+                                  % (points, len(times), cores)), best
 
 
 def ref_autograd_on_gpu(theta, dev, n=1 << 18):
@@ -151,37 +163,45 @@ def dense_grid_inference(dev, n_axis=464):
     pts = float(n_axis) ** 3
     # fixed-R inference: 6 656 FLOP/point
     return {"value": pts / (ms * 1e-3), "unit": "points/s", "ms": ms, "grid": "%d^3" % n_axis,
-            "E_int": r["psiHpsi"] / r["psi2"], "frac_of_fp32_peak": 6656.0 * pts / (ms * 1e-3) / FP32_PEAK_MEASURED}
+            "E_int": r["psiHpsi"] / r["psi2"], "flop_per_point": 6656.0, "tflops": 6656.0 * pts / (ms * 1e-3) / 1e12}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only): float64 nested
+    autograd (oracle/ref_autograd.py, pinned to the real reference by tests/test_oracle.py) on the SAME workload as the
+    GPU arm - one full batch of --points (2^18) points per step, --steps steps, all host threads (set explicitly).  The
+    step count is only clipped if the run would exceed ~3 minutes (0.4 s per step on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     theta = load_theta()
     import torch
     from oracle import ref_autograd as ra
-    cores = torch.get_num_threads()
-    ns = 1 << 16
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    ns = args.points
     g = torch.Generator().manual_seed(1234)
     x, y, z, R, i1, i2 = ra.sample_box(ns, "poc", g)
     th = torch.tensor(theta, dtype=torch.float64)
-    for _ in range(max(1, min(args.warmup, 3))):
+    t0 = time.time()
+    ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
+    t_first = time.time() - t0
+    W = max(0, min(args.warmup, 3) - 1)
+    for _ in range(W):
         ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
-    steps = max(1, min(args.steps, 40))
+    steps = max(1, min(args.steps, int(180.0 / max(t_first, 1e-3))))
     t0 = time.time()
     for _ in range(steps):
         ra.loss_and_grad("poc", th, x, y, z, R, i1, i2)
     dt = (time.time() - t0) / steps
     v = ns / dt
-    sample = "each step = %d-point sample of the 2^18-point batch; float64 nested autograd (oracle/ref_autograd.py)" % ns
+    sample = ("each step = one full batch of %d points; float64 nested autograd (oracle/ref_autograd.py), %d threads; "
+              "%d of the %d requested steps timed" % (ns, cores, steps, args.steps))
     emit({
         "impl": "reference", "metric": "collocation points/sec per training step (fwd+lap+bwd)", "value": v,
-        "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": W + 1, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)",
-                   "sample_points": ns},
+        "config": {"workload": WORKLOAD, "points_per_gpu": ns, "host_threads": cores},
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -240,6 +260,165 @@ def tensor_ceiling(flop_per_launch, kernel_ms):
     return {"achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src}
 
 
+def kernel_source_sha256():
+    """Hash of the sources the step kernel is compiled from: ties the committed ncu figures (profiles/traffic.json) to a build."""
+    import hashlib
+    hsh = hashlib.sha256()
+    csrc = os.path.join(ROOT, "pinn_for_quantum_wavefunction_surfaces_b200", "csrc")
+    for f in ("pinn_step_tc.cu", "pinn_tc.cuh", "pinn_device.cuh", "pinn_common.cuh", "pinn_launch.h"):
+        with open(os.path.join(csrc, f), "rb") as fh:
+            hsh.update(fh.read())
+    return hsh.hexdigest()
+
+
+def committed_ncu_figures():
+    """roofline.traffic / pipe utilisation come from ONE `ncu --set full` capture (a number taken under a profiler cannot be
+    produced inside a timed run).  profiles/traffic.json records the hash of the kernel sources it was captured from; when
+    the sources have changed since, the figures are withheld instead of silently describing another kernel."""
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tf):
+        return None, None, "no capture committed"
+    tj = json.load(open(tf))
+    now = kernel_source_sha256()
+    if tj.get("kernel_source_sha256") != now:
+        return None, None, ("stale: profiles/traffic.json was captured from kernel sources %s, this build is %s"
+                            % (str(tj.get("kernel_source_sha256"))[:12], now[:12]))
+    return tj.get("dram_bytes_per_launch"), tj.get("ncu_pipe_utilisation_pct"), "%s (kernel sources %s)" % (tj.get("source"), now[:12])
+
+
+def dp_parity_check(pk, dp, dist, h, dev, rank, world, theta, n=1 << 18):
+    """Correctness of the fused exchange where the driver can see it (N > 1), before anything is timed: every rank evaluates
+    ITS SHARD of one common seeded batch through the fused exchange; the result must be bit-identical on all ranks, equal to
+    the same shards summed by an NCCL all-reduce (same arithmetic, other transport: 1e-12) and equal to one GPU evaluating
+    the whole batch alone (other tiling of the float32 partial sums: 1e-6).  Returns the dict for the JSON line."""
+    import torch
+    b = synth_batch(n, 777)                       # identical on every rank
+    r1 = torch.sqrt((b[0] - b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+    r2 = torch.sqrt((b[0] + b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+    w = torch.tensor([1.0 / n, 1.0 / float((r1 >= 17.5).sum()), 1.0 / float((r2 >= 17.5).sum())], dtype=torch.float64, device=dev)
+    per = n // world
+    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else n
+    sh = [b[k, lo:hi].contiguous().to(dev) for k in range(4)]
+    full = [b[k].contiguous().to(dev) for k in range(4)]
+
+    def evaluate(cols):
+        out = torch.zeros(dp.N_OUT, dtype=torch.float64, device=dev)
+        pk.loss_and_grad_raw(0, cols[0], cols[1], cols[2], cols[3], theta, None, w, sums=out[:8], dtheta=out[8:])
+        return out
+    fused = evaluate(sh)                          # exchange enabled: global sums on every rank
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(fused) for _ in range(world)]
+    dist.all_gather(gathered, fused)
+    bitwise = all(torch.equal(gathered[0].view(torch.int64), g.view(torch.int64)) for g in gathered[1:])
+    h.dp_enable(False)
+    local = evaluate(sh)
+    dist.all_reduce(local)                        # the same shards through NCCL
+    single = evaluate(full)                       # one GPU, whole batch (every rank does it; rank 0's is reported)
+    torch.cuda.synchronize()
+    dist.barrier()
+    h.dp_enable(True)
+    rel = lambda a, c: float((a - c).abs().max() / c.abs().max())
+    res = {"points": n, "bitwise_equal_across_ranks": bool(bitwise),
+           "rel_sums_vs_nccl_allreduce": rel(fused[:7], local[:7]), "rel_grad_vs_nccl_allreduce": rel(fused[8:], local[8:]),
+           "rel_sums_vs_single_gpu": rel(fused[:7], single[:7]), "rel_grad_vs_single_gpu": rel(fused[8:], single[8:]),
+           "bars": {"vs_nccl_allreduce": 1e-12, "vs_single_gpu": 1e-6}}
+    res["ok"] = bool(bitwise and res["rel_sums_vs_nccl_allreduce"] < 1e-12 and res["rel_grad_vs_nccl_allreduce"] < 1e-12 and
+                     res["rel_sums_vs_single_gpu"] < 1e-6 and res["rel_grad_vs_single_gpu"] < 1e-6)
+    flag = torch.tensor([1 if res["ok"] else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok_on_all_ranks"] = bool(int(flag.item()))
+    return res
+
+
+def seam_e2e(pk, dev, n, steps):
+    """The drop-in boundary itself, timed: the reference's training-loop body (poc/main.py:394-411) - zero_grad,
+    model.LossFunctions (patched: pk.patch_nn_ion), Ltot.backward(), torch.optim.Adam.step(), the four .cpu() reads of the
+    history lines - on an nn.Module with NN_ion's parameter set (same names, shapes, order; float64 like the reference),
+    batches of n points as (n,1) float64 tensors with torch.where index tuples.  Sampling is the reference's own code and
+    is not part of the seam, so batches are drawn up front: 8 rotating batches (every step sees index tensors the mask cache
+    does not hold = the resampling phase of the loop) and one frozen batch (the last 10 % of the reference's epochs)."""
+    import torch
+    import torch.nn as nn
+    from pinn_for_quantum_wavefunction_surfaces_b200 import convert
+
+    class IonParams(nn.Module):
+        def __init__(self, theta):
+            super().__init__()
+            mk = lambda i, o: nn.Linear(i, o, dtype=torch.float64)
+            self.Lin_H1, self.Lin_H2, self.Lin_out = mk(2, 16), mk(16, 16), mk(16, 1)
+            self.Lin_E1, self.Lin_E2, self.Lin_Eout = mk(1, 32), mk(32, 32), mk(32, 1)
+            self.netDecayL, self.netDecay = mk(1, 10), mk(10, 1)
+            self.P, self.Ry, self.Rz = 1, 0, 0
+            self.load_state_dict(convert.state_dict_from_theta(theta))
+    assert [k for k, _ in IonParams(load_theta()).named_parameters()] == pk.POC_TENSOR_NAMES
+    pk.patch_nn_ion(IonParams)
+    params = {"BCcutoff": 17.5, "inversion_symmetry": 1, "Ry": 0, "Rz": 0}
+
+    def batches(device, nb, pin=False):
+        out = []
+        for k in range(nb):
+            b = synth_batch(n, 5000 + k).double()
+            cols = [b[j].reshape(n, 1).contiguous() for j in range(4)]
+            if pin:
+                cols = [c.pin_memory() for c in cols]
+            cols = [c.to(device) for c in cols] if device.type == "cuda" else cols
+            r1 = torch.sqrt((cols[0] - cols[3]) ** 2 + cols[1] ** 2 + cols[2] ** 2)
+            r2 = torch.sqrt((cols[0] + cols[3]) ** 2 + cols[1] ** 2 + cols[2] ** 2)
+            out.append(cols + [torch.where(r1 >= 17.5), torch.where(r2 >= 17.5)])
+        return out
+
+    def loop(device, bs, K):
+        model = IonParams(load_theta()).to(device)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-7, weight_decay=0)
+        hist = np.zeros((K + 5, 4))
+        split = {"LossFunctions": 0.0, "backward": 0.0, "optimizer.step": 0.0, "history .cpu()": 0.0}
+        pc = time.perf_counter
+        for tt in range(K + 5):
+            if tt == 5:                                  # 5 untimed steps first
+                if device.type == "cuda":
+                    torch.cuda.synchronize()
+                split = {k: 0.0 for k in split}
+                t_start = pc()
+            x, y, z, R, b1, b2 = bs[tt % len(bs)]
+            opt.zero_grad()
+            t0 = pc()
+            Ltot, LossPDE, Lbc, E = model.LossFunctions(x, y, z, R, params, b1, b2)
+            t1 = pc()
+            Ltot.backward(retain_graph=False)
+            t2 = pc()
+            opt.step()
+            t3 = pc()
+            hist[tt, 0] = Ltot.cpu().data.numpy(); hist[tt, 1] = LossPDE.cpu().data.numpy()
+            hist[tt, 2] = Lbc.cpu().data.numpy(); hist[tt, 3] = E[-1].cpu().data.numpy()
+            t4 = pc()
+            split["LossFunctions"] += t1 - t0; split["backward"] += t2 - t1
+            split["optimizer.step"] += t3 - t2; split["history .cpu()"] += t4 - t3
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+        dt = (pc() - t_start) / K
+        return {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": K, "loss": float(hist[-1, 0]),
+                "host_ms_per_step": {k: round(v / K * 1e3, 4) for k, v in split.items()}}
+    cpu = torch.device("cpu")
+    n_small = n
+    res = {"cuda_resident": loop(dev, batches(dev, 8), steps),
+           "cuda_resident_frozen_batch": loop(dev, batches(dev, 1), steps),
+           "cpu_resident_pageable": loop(cpu, batches(cpu, 8), max(5, steps // 4)),
+           "cpu_resident_pinned": loop(cpu, batches(cpu, 8, pin=True), max(5, steps // 4)),
+           "e2e_fraction_note": "per step the loop spends ~0.26 ms in torch.optim.Adam.step and ~0.1 ms in the four .cpu() reads on the "
+                                "host - the reference's own lines - against 0.14 ms for a whole e2e step; the seam is host-bound at "
+                                "2^18 points and GPU-bound from ~2^21 points per step on (cuda_resident_4M_points)",
+           "what": "reference loop body (poc/main.py:394-411) on the patched LossFunctions: zero_grad, LossFunctions, backward, "
+                   "torch.optim.Adam.step, 4 history reads with .cpu(); float64 (n,1) tensors + torch.where index tuples; "
+                   "host_ms_per_step splits the wall time by line (the .cpu() line absorbs the wait for the GPU)"}
+    n = 1 << 22                      # BASELINE config 4's batch on one GPU: the host work hides behind the kernel
+    res["cuda_resident_4M_points"] = loop(dev, batches(dev, 3), max(10, steps // 4))
+    n = n_small
+    return res
+
+
+WORKLOAD = "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)"
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -248,10 +427,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1 << 18, help="collocation points per GPU per step")
+    ap.add_argument("--global-points", type=int, default=1 << 22,
+                    help="BASELINE config 4: points per step of the WHOLE job, sharded over the ranks (extra key config4_global_batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "ffma"],
-                    help="implementation of the fused step kernel (include/pinn_b200.h: pinn_set_engine)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the headline timed regions (profiling runs): no e2e / seam / config-4 / training-loop legs")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
                     help="N>1: sum over ranks fused into the reduction kernel over NVLink peer memory (pinn_dp_*), or a "
                          "separate NCCL all-reduce per step (the baseline it replaces)")
@@ -277,7 +458,6 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     h = pk.Handle.get(local)
-    h.set_engine(args.engine)
     fused = world > 1 and args.allreduce == "fused"
     if fused and not dp.attach_fused(h, strict=False):
         fused = False   # all ranks agreed: no peer mapping on this box -> the NCCL all-reduce path (reported in config)
@@ -285,27 +465,59 @@ def main():
             print("bench: fused exchange unavailable, falling back to --allreduce nccl", file=sys.stderr)
 
     theta = torch.from_numpy(load_theta().astype(np.float32)).to(dev)
-    host_batches = [synth_batch(n, 1000 * rank + b).pin_memory() for b in range(N_BATCHES)]
-    dev_batches = [b.to(dev) for b in host_batches]
-    out = torch.zeros(dp.N_OUT, dtype=torch.float64, device=dev)
-    # boundary sets are derived in-kernel (r >= 17.5); their global sizes for the 1/count weights come from a
-    # count pass per batch done up front (the sampler knows them in a real run)
-    wts = []
-    for b in host_batches:   # on the host, so that the only kernels this process launches are the library's own
-        r1 = torch.sqrt((b[0] - b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
-        r2 = torch.sqrt((b[0] + b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
-        wts.append(dp.global_weights(n, int((r1 >= 17.5).sum()), int((r2 >= 17.5).sum()), device=dev))
+    parity = None
+    if fused:
+        parity = dp_parity_check(pk, dp, dist, h, dev, rank, world, theta)
+        if not parity["ok_on_all_ranks"]:
+            if rank == 0:
+                emit({"metric": "collocation points/sec per training step (fwd+lap+bwd)", "value": None, "n_gpus": world,
+                      "dp_parity": parity, "error": "data-parallel parity check failed; nothing was timed"})
+            raise SystemExit(3)
 
-    def step(i):
-        b = dev_batches[i % N_BATCHES]
-        pk.loss_and_grad_raw(0, b[0], b[1], b[2], b[3], theta, None, wts[i % N_BATCHES], sums=out[:8], dtheta=out[8:])
-        if world > 1 and not fused:
-            dist.all_reduce(out)
+    def make_batches(npts, nb, seed0):
+        hb = [synth_batch(npts, seed0 + 1000 * rank + b).pin_memory() for b in range(nb)]
+        db = [b.to(dev) for b in hb]
+        # boundary sets are derived in-kernel (r >= 17.5); their global sizes for the 1/count weights come from a count
+        # pass per batch done up front on the host (the sampler knows them in a real run), so that the only kernels this
+        # process launches are the library's own
+        ws = []
+        for b in hb:
+            r1 = torch.sqrt((b[0] - b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+            r2 = torch.sqrt((b[0] + b[3]) ** 2 + b[1] ** 2 + b[2] ** 2)
+            ws.append(dp.global_weights(npts, int((r1 >= 17.5).sum()), int((r2 >= 17.5).sum()), device=dev))
+        return hb, db, ws
+    host_batches, dev_batches, wts = make_batches(n, N_BATCHES, 0)
+    out = torch.zeros(dp.N_OUT, dtype=torch.float64, device=dev)
+
+    def make_step(db, ws):
+        nb = len(db)
+
+        def step(i):
+            b = db[i % nb]
+            pk.loss_and_grad_raw(0, b[0], b[1], b[2], b[3], theta, None, ws[i % nb], sums=out[:8], dtheta=out[8:])
+            if world > 1 and not fused:
+                dist.all_reduce(out)
+        return step
+    step = make_step(dev_batches, wts)
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(stepfn, first, count):
+        """`count` steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        e0.record()
+        for i in range(count):
+            stepfn(first + i)
+        e1.record()
+        fence()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for i in range(W):
         step(i)
@@ -313,146 +525,173 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
-    # Two back-to-back timed regions of the same K steps (clocks sampled over both): the first without any extra
-    # stream operation gives `value`; the second brackets every step-kernel launch with CUDA events on the launching
-    # stream (pinn_profile_begin/collect) and gives the kernel's average duration for the roofline.  (The event
-    # records sit between the step kernel and its programmatic-dependent reduction kernel and cost a few
-    # microseconds per step, which is why they are kept out of the first region.)
+    # the clock sampler needs ~0.15 s to deliver its first rows: the GPU keeps stepping meanwhile (more warm-up) instead of
+    # idling, so that the timed region starts on a busy, clocked-up device straight after the fence
+    t_spin = time.time()
+    i_spin = W
+    while time.time() - t_spin < 0.25:
+        for _ in range(20):
+            step(i_spin)
+            i_spin += 1
+        torch.cuda.synchronize()
+    # Two back-to-back timed regions of the same K steps (clocks sampled over both): the first without any extra stream
+    # operation gives `value`; the second brackets every step-kernel launch with CUDA events on the launching stream
+    # (pinn_profile_begin/collect) and gives the kernel's average duration for the roofline.  (The event records sit
+    # between the step kernel and its programmatic-dependent reduction kernel and cost a few microseconds per step, which
+    # is why they are kept out of the first region.)
     launches0 = h.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
     t0 = time.time()
-    e0.record()
-    for i in range(K):
-        step(W + i)
-    e1.record()
-    fence()
-    ms = e0.elapsed_time(e1)
+    ms = timed(step, i_spin, K)
     launches = h.launch_count() - launches0
     h.profile_begin()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(K):
-        step(W + K + i)
-    p1.record()
-    fence()
-    t1 = time.time()
-    ms_profiled = p0.elapsed_time(p1)
+    ms_profiled = timed(step, i_spin + K, K)
     kern_ms, kern_n = h.profile_collect()
+    # the roofline's denominator, measured now on this device (clock samples of the same window)
+    fp32_peak, fp32_ms = h.measure_fp32_peak()
+    steady = None
+    if not args.no_extras:
+        Ks = max(K, 1000)
+        steady = {"value": float(n) * world * Ks / (timed(step, i_spin + 2 * K, Ks) * 1e-3), "unit": "points/s", "steps": Ks}
+    t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     loss = float(out[0].item())
+    line_extra = {}
 
-    # ---- end to end: host buffers through the C ABI (H2D of the batch, kernel, D2H of loss+gradient), every step
-    th64 = np.ascontiguousarray(load_theta())
-    wts_h = [np.ascontiguousarray(w.cpu().numpy()) for w in wts]   # the caller's sampler knows the set sizes
-    # the public call of a host-resident caller: one prepared HostStep per (reused, pinned) batch buffer
-    host_steps = [pk.HostStep("poc", b[0], b[1], b[2], b[3], device=local) for b in host_batches]
+    if not args.no_extras:
+        # ---- end to end: host buffers through the C ABI (H2D of the batch, kernel, D2H of loss+gradient), every step
+        th64 = np.ascontiguousarray(load_theta())
+        wts_h = [np.ascontiguousarray(w.cpu().numpy()) for w in wts]   # the caller's sampler knows the set sizes
+        # the public call of a host-resident caller: one prepared HostStep per (reused, pinned) batch buffer
+        host_steps = [pk.HostStep("poc", b[0], b[1], b[2], b[3], device=local) for b in host_batches]
 
-    def e2e_step(i):
-        sums_h, dth_h = host_steps[i % N_BATCHES](th64, wts_h[i % N_BATCHES])
-        if world > 1 and not fused:
-            out[:8] = torch.from_numpy(sums_h).to(dev)
-            out[8:] = torch.from_numpy(dth_h).to(dev)
-            dist.all_reduce(out)
+        def e2e_step(i):
+            sums_h, dth_h = host_steps[i % N_BATCHES](th64, wts_h[i % N_BATCHES])
+            if world > 1 and not fused:
+                out[:8] = torch.from_numpy(sums_h).to(dev)
+                out[8:] = torch.from_numpy(dth_h).to(dev)
+                dist.all_reduce(out)
 
-    Ke = max(3, min(K, 200))
-    for i in range(N_BATCHES + 3):   # one pass over every page-locked batch buffer first (the GPU's first touch of a
-        e2e_step(i)                  # host page is slower), then the timed calls
-    fence()
-    te0 = time.time()
-    for i in range(Ke):
-        e2e_step(N_BATCHES + 3 + i)
-    fence()
-    te = (time.time() - te0) / Ke
-    e2e_split = h.host_timing()   # of the last call
-    h.profile_begin()             # the kernel's share, measured on a few more calls outside the timed loop
-    for i in range(10):
-        e2e_step(N_BATCHES + 3 + Ke + i)
-    fence()
-    e2e_kern_ms, e2e_kern_n = h.profile_collect()
-    tte = torch.tensor([te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tte, op=dist.ReduceOp.MAX)
-    te = float(tte.item())
+        Ke = max(3, min(K, 200))
+        for i in range(N_BATCHES + 3):   # one pass over every page-locked batch buffer first (the GPU's first touch of a
+            e2e_step(i)                  # host page is slower), then the timed calls
+        fence()
+        te0 = time.time()
+        for i in range(Ke):
+            e2e_step(N_BATCHES + 3 + i)
+        fence()
+        te = (time.time() - te0) / Ke
+        e2e_split = h.host_timing()   # of the last call
+        h.profile_begin()             # the kernel's share, measured on a few more calls outside the timed loop
+        for i in range(10):
+            e2e_step(N_BATCHES + 3 + Ke + i)
+        fence()
+        e2e_kern_ms, e2e_kern_n = h.profile_collect()
+        tte = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tte, op=dist.ReduceOp.MAX)
+        te = float(tte.item())
+        line_extra["e2e"] = {
+            "value": float(n) * world / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
+            "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke,
+            "kernel_ms": e2e_kern_ms / max(e2e_kern_n, 1), "last_call_us": {k: round(v, 1) for k, v in e2e_split.items()},
+            "api": "HostStep -> pinn_loss_fwd_bwd_host (pinned float32 host batches read in place by the kernel: bulk copies "
+                   "(cp.async.bulk) of the next super-tile's columns over PCIe while the current one is computed; pageable "
+                   "inputs are staged in up to 4 chunks)"}
+        del host_steps
 
-    # ---- the whole training loop on the device (sampler -> loss/gradient -> Adam, CUDA-graph replay): N=1 only
-    loop = None
-    if world == 1 or fused:
-        tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6, device=local)
-        Kl = max(10, min(K, 300))
-        ts = torch.cuda.ExternalStream(tr.h.L.pinn_trainer_stream(tr.t), device=dev)
-        res = {}
-        for graph in (False, True):
-            tr.run(20, use_graph=graph)
-            tr.read()
-            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            l0.record(ts)
-            tr.run(Kl, use_graph=graph)
-            l1.record(ts)
-            tr.read()
-            lms = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(lms, op=dist.ReduceOp.MAX)
-            res[graph] = n * world * Kl / (float(lms.item()) * 1e-3)
-        loop = {"value": res[False], "unit": "points/s", "steps": Kl, "value_with_cuda_graph_replay": res[True],
+        # ---- BASELINE config 4 as written: 2^22 points per step of the whole job, sharded over the ranks
+        G = args.global_points
+        n4 = G // world
+        nb4 = max(4, -(-160_000_000 // (16 * n4)))      # rotating batches: > 126 MB L2 in total
+        _, db4, w4 = make_batches(n4, nb4, 7000)
+        # (make_batches -> dp.global_weights: the weights of a sharded batch are those of the GLOBAL batch)
+        step4 = make_step(db4, w4)
+        for i in range(3):
+            step4(i)
+        K4 = max(3, min(K, 200))
+        ms4 = timed(step4, 3, K4)
+        line_extra["config4_global_batch"] = {
+            "value": float(n4) * world * K4 / (ms4 * 1e-3), "unit": "points/s", "global_points": int(n4 * world),
+            "points_per_gpu": int(n4), "ms_per_step": ms4 / K4, "steps": K4, "scaling": "strong",
+            "inputs": "%d rotating batches of %.1f MB per GPU resident in HBM" % (nb4, 16 * n4 / 1e6),
+            "what": "BASELINE config 4: 2^22 collocation points per step sharded over the ranks, one fused exchange per step"}
+        del db4
+
+        # ---- the whole training loop on the device (sampler -> loss/gradient -> Adam, CUDA-graph replay)
+        if world == 1 or fused:
+            tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6, device=local)
+            Kl = max(10, min(K, 300))
+            ts = torch.cuda.ExternalStream(tr.h.L.pinn_trainer_stream(tr.t), device=dev)
+            res = {}
+            for graph in (False, True):
+                tr.run(20, use_graph=graph)
+                tr.read()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record(ts)
+                tr.run(Kl, use_graph=graph)
+                l1.record(ts)
+                tr.read()
+                lms = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+                res[graph] = n * world * Kl / (float(lms.item()) * 1e-3)
+            line_extra["device_train_loop"] = {
+                "value": res[False], "unit": "points/s", "steps": Kl, "value_with_cuda_graph_replay": res[True],
                 "what": "pinn_trainer: per step the fused loss/gradient kernel and one kernel with reduction%s + float64 Adam + "
                         "Philox sampler of the next batch, launched as programmatic dependents, no host sync"
                         % (" + set-size and gradient exchange over NVLink" if world > 1 else "")}
-        tr.close()
+            tr.close()
 
-    # ---- two more reference points for N = 1 (BASELINE configs 2 and 5) ----
-    extra = {}
-    if world == 1 and not args.no_cpu_baseline:
-        extra["reference_autograd_on_gpu"] = ref_autograd_on_gpu(load_theta(), dev)
-        extra["dense_grid_inference"] = dense_grid_inference(dev)
+        # ---- N = 1: the seam itself, and two more reference points (BASELINE configs 2 and 5)
+        if world == 1:
+            line_extra["seam_e2e"] = seam_e2e(pk, dev, n, max(20, min(K, 100)))
+            if not args.no_cpu_baseline:
+                line_extra["reference_autograd_on_gpu"] = ref_autograd_on_gpu(load_theta(), dev)
+                line_extra["dense_grid_inference"] = dense_grid_inference(dev)
 
     if rank == 0:
         total_points = float(n) * world
         value = total_points * K / (ms * 1e-3)
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = FLOP_PER_POINT * n / (kern_avg_ms * 1e-3)
-        traffic, ncu_pipes = None, None
-        tf = os.path.join(ROOT, "profiles", "traffic.json")   # numbers of the committed ncu --set full capture of this kernel
-        if os.path.exists(tf) and args.engine == "tcgen05":
-            tj = json.load(open(tf))
-            traffic, ncu_pipes = tj.get("dram_bytes_per_launch"), tj.get("ncu_pipe_utilisation_pct")
+        traffic, ncu_pipes, ncu_src = committed_ncu_figures()
         line = {
             "metric": "collocation points/sec per training step (fwd+lap+bwd)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "ms_per_step_with_kernel_events": ms_profiled / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ionHsym poc-form training step, 2^18 collocation points/step/GPU (BASELINE config 3)",
+            "config": {"workload": WORKLOAD,
                        "points_per_gpu": n, "global_points": int(total_points), "weights": "models/ionHsym.pt (tests/golden/checkpoints.npz)",
                        "inputs": "%d rotating batches resident in HBM, %.0f MB > 126 MB L2" % (N_BATCHES, N_BATCHES * n * 16 / 1e6),
+                       "warmup_note": "%d warm-up steps, then %d more untimed steps while the clock sampler starts (no idle gap in front of the timed region)" % (W, i_spin - W),
                        "parallelism": ("dp%d point sharding; sum of 1529 f64 over ranks %s" % (
                            world, "fused into the reduction kernel (NVLink peer stores + flags, pinn_dp_*)" if fused
                            else "by one NCCL all-reduce per step")) if world > 1 else "single GPU"},
-            "roofline": {"bound": "fp32_ffma", "achieved": achieved / 1e12, "peak": FP32_PEAK_MEASURED / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_MEASURED,
+            "roofline": {"bound": "fp32_ffma", "achieved": achieved / 1e12, "peak": fp32_peak / 1e12,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "frac_of_nominal_74.4": achieved / FP32_PEAK_NOMINAL,
-                         "peak_source": "measured FFMA rate on this pool's B200 (tools/microbench/pipes.cu); MEASURED_PEAKS.json has no FP32 entry",
-                         "flop_per_point": FLOP_PER_POINT, "engine": args.engine,
-                         "kernel": "pinn_step_tc_kernel<2,true>" if args.engine == "tcgen05" else "pinn_step_kernel<2,4,true>",
+                         "peak_source": "FFMA rate measured in this run on this device (pinn_measure_fp32_peak: register-resident "
+                                        "FFMA loop, %.3f ms per timed kernel, clocks in `clocks`); MEASURED_PEAKS.json has no FP32 entry; "
+                                        "round-1 figure of the same loop: %.1f" % (fp32_ms, FP32_PEAK_FALLBACK / 1e12),
+                         "flop_per_point": FLOP_PER_POINT,
+                         "kernel": "pinn_step_tc_kernel<2,true,false>",
                          "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes,
+                         "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes, "ncu_source": ncu_src,
                          "vs_hbm_ceiling": hbm_ceiling(16 * n, kern_avg_ms),
                          "vs_3xtf32_tensor_ceiling": tensor_ceiling(FLOP_PER_POINT * n, kern_avg_ms)},
-            "e2e": {"value": total_points / te, "unit": "points/s", "h2d_bytes_per_step": int(16 * n + 1521 * 4),
-                    "d2h_bytes_per_step": int((8 + 1521) * 8), "ms_per_step": te * 1e3, "steps": Ke, "kernel_ms": e2e_kern_ms / max(e2e_kern_n, 1),
-                    "last_call_us": {k: round(v, 1) for k, v in e2e_split.items()},
-                    "api": "HostStep -> pinn_loss_fwd_bwd_host (pinned float32 host batches read in place by the kernel: cp.async of the next super-tile over PCIe while the current one is computed; pageable inputs are staged in up to 4 chunks)"},
             "gpu_launches": int(launches), "clocks": clocks, "loss": loss,
         }
-        if loop:
-            line["device_train_loop"] = loop
-        line.update(extra)
-        if not args.no_cpu_baseline and world == 1:
-            v, cores, sample, _ = cpu_reference_points_per_s(th64, args.cpu_seconds)
+        if steady:
+            line["value_steady"] = steady
+        if parity:
+            line["dp_parity"] = parity
+        line.update(line_extra)
+        if "e2e" not in line:
+            line["e2e"] = None
+        if "dense_grid_inference" in line:
+            line["dense_grid_inference"]["frac_of_fp32_peak"] = line["dense_grid_inference"]["tflops"] * 1e12 / fp32_peak
+        if not args.no_cpu_baseline and world == 1 and not args.no_extras:
+            v, cores, sample, _ = cpu_reference_points_per_s(np.ascontiguousarray(load_theta()), args.cpu_seconds, n)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
         emit(line)
     if fused:

@@ -83,6 +83,11 @@ int64_t pinn_launch_count(pinn_handle* h);
 int pinn_set_engine(pinn_handle* h, int engine);
 int pinn_get_engine(pinn_handle* h);
 
+/* Measurement helper (bench.py's roofline denominator): the FP32 FFMA rate of this device right now, from a
+ * register-resident loop of independent FFMA chains (best of 5 timings of ~0.3 ms each, CUDA events).
+ * fma_per_s: fused multiply-adds per second (x2 = FLOP/s); ms: duration of one timed kernel.  Synchronous. */
+int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms);
+
 /* Host-side wall-clock split of the last pinn_loss_fwd_bwd_host call on this handle, microseconds:
  * {enqueue (argument checks, parameter conversion, launches), wait for the device, copy-out, total}. */
 int pinn_host_timing(pinn_handle* h, double* out4);
@@ -134,6 +139,37 @@ int pinn_fields(pinn_handle* h, int variant, int64_t n,
                 const void* x, const void* y, const void* z, const void* R, int in_dtype,
                 const float* theta,
                 float* psi, float* lap, float* hpsi, float* res, float* E, void* stream);
+
+/*
+ * pinn_loss_fwd_bwd for a caller that holds the model as its 16 PARAMETER TENSORS (an nn.Module / train.py's tuple) -
+ * the call behind the torch.autograd.Function that replaces NN_ion.LossFunctions (poc/main.py:341-355) and the inline
+ * block train.py:41-57.  Nothing is packed or converted in front of the launch:
+ *  params        16 device pointers, one per tensor, in the order and layout named by param_layout:
+ *                PINN_VARIANT_POC     = NN_ion.state_dict() order, nn.Linear (out,in) weights (poc/main.py:233-245)
+ *                PINN_VARIANT_TRAINPY = train.py's tuple order (gate before E-net), (in,out) weights (train.py:88-109)
+ *                every CTA of the step kernel gathers them (and converts float64 -> float32) while it builds its
+ *                operand images
+ *  param_dtype   PINN_F32 / PINN_F64 (all 16 alike)
+ *  weights_host  HOST, 3 double {w_pde, w_bc1, w_bc2}: carried inside the kernel parameters; NULL = counted on the device
+ *  dtheta        device, 1521 double, the tensors in canonical ORDER (pinn_theta_offsets) but each in the caller's
+ *                LAYOUT ((in,out) for PINN_VARIANT_TRAINPY), so that per-tensor views need no transpose
+ *  E_out         device, n values of E_dtype (PINN_F32 / PINN_F64) or NULL
+ * Everything else as in pinn_loss_fwd_bwd.
+ */
+int pinn_loss_fwd_bwd_tensors(pinn_handle* h, int variant, int64_t n,
+                              const void* x, const void* y, const void* z, const void* R, int in_dtype,
+                              const uint8_t* mask, const void* const* params, int param_dtype, int param_layout,
+                              const double* weights_host, uint32_t grad_mask, float bcutoff,
+                              double* sums, double* dtheta, void* E_out, int E_dtype, void* stream);
+
+/*
+ * The reference passes the two boundary sets as index tensors (torch.where(r >= BCcutoff), poc/main.py:392-393;
+ * train.py:38-39); the kernels want one byte per point.  idx1 / idx2: device int64 row indices (n1 / n2 of them);
+ * mask: device, 4-byte aligned, room for n rounded up to a multiple of 4 bytes; bit 0 = set 1, bit 1 = set 2.
+ * One memset + one kernel on `stream`.
+ */
+int pinn_mask_from_index_sets(pinn_handle* h, int64_t n, const int64_t* idx1, int64_t n1, const int64_t* idx2, int64_t n2,
+                              uint8_t* mask, void* stream);
 
 /*
  * Same as pinn_loss_fwd_bwd but with HOST buffers (the call a CPU-resident caller such

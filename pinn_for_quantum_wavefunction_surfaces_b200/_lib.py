@@ -10,6 +10,7 @@ _LIB_NAME = "libpinn_b200.so"
 EXPORTS = [
     "pinn_version", "pinn_theta_size", "pinn_theta_offsets", "pinn_create", "pinn_destroy", "pinn_last_error",
     "pinn_launch_count", "pinn_set_engine", "pinn_get_engine", "pinn_profile_begin", "pinn_profile_collect", "pinn_loss_fwd_bwd", "pinn_fields", "pinn_loss_fwd_bwd_host",
+    "pinn_loss_fwd_bwd_tensors", "pinn_mask_from_index_sets", "pinn_measure_fp32_peak",
     "pinn_sample", "pinn_adam_step", "pinn_enet_curve", "pinn_grid_reduce", "pinn_trainer_create", "pinn_trainer_destroy",
     "pinn_trainer_load_state", "pinn_trainer_set_batch", "pinn_trainer_run", "pinn_trainer_read", "pinn_trainer_batch",
     "pinn_trainer_stream",
@@ -75,6 +76,12 @@ def lib():
         L.pinn_profile_collect.restype = i32
         L.pinn_loss_fwd_bwd.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, u32, f32, vp, vp, vp, vp]
         L.pinn_loss_fwd_bwd.restype = i32
+        L.pinn_loss_fwd_bwd_tensors.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp, u32, f32, vp, vp, vp, i32, vp]
+        L.pinn_loss_fwd_bwd_tensors.restype = i32
+        L.pinn_mask_from_index_sets.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp]
+        L.pinn_mask_from_index_sets.restype = i32
+        L.pinn_measure_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.pinn_measure_fp32_peak.restype = i32
         L.pinn_fields.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.pinn_fields.restype = i32
         L.pinn_loss_fwd_bwd_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, u32, f32, vp, vp, vp]
@@ -162,6 +169,12 @@ class Handle:
 
     def get_engine(self):
         return {v: k for k, v in self.ENGINES.items()}[int(self.L.pinn_get_engine(self.h))]
+
+    def measure_fp32_peak(self):
+        """-> (FLOP/s of the FP32 FFMA pipe measured now on this device, milliseconds of one timed kernel)"""
+        r, ms = ctypes.c_double(), ctypes.c_double()
+        self.check(self.L.pinn_measure_fp32_peak(self.h, ctypes.byref(r), ctypes.byref(ms)), "pinn_measure_fp32_peak")
+        return 2.0 * r.value, ms.value
 
     def profile_begin(self):
         self.check(self.L.pinn_profile_begin(self.h), "pinn_profile_begin")

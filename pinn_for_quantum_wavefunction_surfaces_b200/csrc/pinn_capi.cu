@@ -416,44 +416,51 @@ static int enqueue_step_chunk(pinn_handle* h, pinn_workspace* ws, int nev, StepP
 // entry) NULL with theta_inline / weights_inline = HOST arrays that travel inside the kernel parameters.
 }  // extern "C"
 
-int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
-                      const void* R, int in_dtype, const uint8_t* mask, const float* theta, const double* weights,
-                      const float* theta_inline, const double* weights_inline, uint32_t grad_mask, float bcutoff,
-                      double* sums, double* dtheta, float* E_out, cudaStream_t st, const AdamParams* adam,
-                      unsigned long long* adam_ticket, const SampleParams* presample) {
+int loss_fwd_bwd_impl(pinn_handle* h, const LossCall& c, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(h->mu);
   StepParams p{};
   int nev = 0;
-  if (variant_coef(variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: unknown variant");
-  if (n <= 0) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: n must be positive");
-  if (!x || !y || !z || !R || (!theta && !theta_inline) || !sums || !dtheta)
+  if (variant_coef(c.variant, &p.vc, &nev)) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: unknown variant");
+  if (c.n <= 0) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: n must be positive");
+  if (!c.x || !c.y || !c.z || !c.R || (!c.theta && !c.theta_inline && !c.theta_tensors) || !c.sums || !c.dtheta)
     return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
-  if (in_dtype != PINN_F32 && in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
+  if (c.in_dtype != PINN_F32 && c.in_dtype != PINN_F64) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: bad in_dtype");
   DevGuard dev_guard(h->device);
   pinn_workspace* ws = ws_for(h, st, h->sm_count);
   if (!ws) return PINN_EINVAL;
   if (int rc = dp_serialize(h, st)) return rc;
-  p.x = x; p.y = y; p.z = z; p.R = R; p.mask = mask; p.n = n; p.in_f64 = in_dtype == PINN_F64;
-  p.bcut = bcutoff; p.partials = ws->partials; p.E_out = E_out;
-  p.base_grads = (grad_mask & 0x003Fu) != 0;
-  p.gate_grads = (grad_mask & 0xF000u) != 0;
-  if (theta_inline) {
-    p.theta_inline = theta_inline;
-    p.weights_inline = weights_inline;
-  } else {
-    if (int rc = enqueue_prep(h, theta, p, st)) return rc;
-    if (!weights) {
-      CU(h, launch_count(p, ws->counts, ws->weights, st));
-      h->launches += 2;
-      weights = ws->weights;
+  p.x = c.x; p.y = c.y; p.z = c.z; p.R = c.R; p.mask = c.mask; p.n = c.n; p.in_f64 = c.in_dtype == PINN_F64;
+  p.bcut = c.bcutoff; p.partials = ws->partials; p.E_out = static_cast<float*>(c.E_out); p.E_f64 = c.E_f64;
+  p.base_grads = (c.grad_mask & 0x003Fu) != 0;
+  p.gate_grads = (c.grad_mask & 0xF000u) != 0;
+  const double* weights = c.weights;
+  if (c.theta_inline) {
+    p.theta_inline = c.theta_inline;
+  } else if (c.theta_tensors) {
+#ifdef PINN_AB_BUILD
+    if (h->engine != PINN_ENGINE_TCGEN05) return fail(h, PINN_ENOTSUP, "the FFMA engine takes a packed theta only");
+#endif
+    for (int k = 0; k < 16; k++) {
+      if (!c.theta_tensors[k]) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_tensors: NULL parameter tensor");
+      p.theta_tensors[k] = c.theta_tensors[k];
     }
+    p.theta_from_tensors = 1; p.tensors_f64 = c.tensors_f64; p.tensors_in_out = c.tensors_in_out;
+  } else {
+    if (int rc = enqueue_prep(h, c.theta, p, st)) return rc;
+  }
+  if (c.weights_inline) {
+    p.weights_inline = c.weights_inline;
+  } else if (!weights) {
+    CU(h, launch_count(p, ws->counts, ws->weights, st));
+    h->launches += 2;
+    weights = ws->weights;
   }
   p.weights = weights;
   int grid = 0;
-  int rc = enqueue_step_chunk(h, ws, nev, p, 0, n, 0, &grid, st);
+  int rc = enqueue_step_chunk(h, ws, nev, p, 0, c.n, 0, &grid, st);
   if (rc) return rc;
-  CU(h, launch_reduce(ws->partials, grid, weights, theta_inline ? weights_inline : nullptr, grad_mask, dtheta, sums, E_out, n,
-                      h->dp_on ? h->dp : DpArgs(), st, adam, adam_ticket, presample));
+  CU(h, launch_reduce(ws->partials, grid, weights, c.weights_inline, c.grad_mask, c.dtheta, c.sums, p.E_out, c.n,
+                      h->dp_on ? h->dp : DpArgs(), st, c.adam, c.adam_ticket, c.presample, c.E_f64, c.dtheta_in_out));
   h->launches++;
   return 0;
 }
@@ -465,8 +472,45 @@ int pinn_loss_fwd_bwd(pinn_handle* h, int variant, int64_t n, const void* x, con
                       uint32_t grad_mask, float bcutoff, double* sums, double* dtheta, float* E_out, void* stream) {
   if (!h) return PINN_EINVAL;
   if (!theta) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd: NULL pointer argument");
-  return loss_fwd_bwd_impl(h, variant, n, x, y, z, R, in_dtype, mask, theta, weights, nullptr, nullptr, grad_mask, bcutoff, sums,
-                           dtheta, E_out, (cudaStream_t)stream);
+  LossCall c;
+  c.variant = variant; c.n = n; c.x = x; c.y = y; c.z = z; c.R = R; c.in_dtype = in_dtype; c.mask = mask;
+  c.theta = theta; c.weights = weights; c.grad_mask = grad_mask; c.bcutoff = bcutoff; c.sums = sums; c.dtheta = dtheta;
+  c.E_out = E_out;
+  return loss_fwd_bwd_impl(h, c, (cudaStream_t)stream);
+}
+
+int pinn_loss_fwd_bwd_tensors(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z,
+                              const void* R, int in_dtype, const uint8_t* mask, const void* const* params, int param_dtype,
+                              int param_layout, const double* weights_host, uint32_t grad_mask, float bcutoff, double* sums,
+                              double* dtheta, void* E_out, int E_dtype, void* stream) {
+  if (!h) return PINN_EINVAL;
+  if (!params) return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_tensors: NULL pointer argument");
+  if ((param_dtype != PINN_F32 && param_dtype != PINN_F64) || (E_dtype != PINN_F32 && E_dtype != PINN_F64) ||
+      (param_layout != PINN_VARIANT_POC && param_layout != PINN_VARIANT_TRAINPY))
+    return fail(h, PINN_EINVAL, "pinn_loss_fwd_bwd_tensors: bad dtype / layout code");
+  // canonical order of the 16 tensors; train.py keeps the gate (L1a..L2b) in front of the E-net (train.py:108-109)
+  static const int kTrainpyToCanonical[16] = {0, 1, 2, 3, 4, 5, 12, 13, 14, 15, 6, 7, 8, 9, 10, 11};
+  const void* canon[16];
+  for (int k = 0; k < 16; k++) canon[param_layout == PINN_VARIANT_TRAINPY ? kTrainpyToCanonical[k] : k] = params[k];
+  LossCall c;
+  c.variant = variant; c.n = n; c.x = x; c.y = y; c.z = z; c.R = R; c.in_dtype = in_dtype; c.mask = mask;
+  c.theta_tensors = canon; c.tensors_f64 = param_dtype == PINN_F64; c.tensors_in_out = param_layout == PINN_VARIANT_TRAINPY;
+  c.weights_inline = weights_host; c.grad_mask = grad_mask; c.bcutoff = bcutoff; c.sums = sums; c.dtheta = dtheta;
+  c.E_out = E_out; c.E_f64 = E_dtype == PINN_F64; c.dtheta_in_out = c.tensors_in_out;
+  return loss_fwd_bwd_impl(h, c, (cudaStream_t)stream);
+}
+
+int pinn_mask_from_index_sets(pinn_handle* h, int64_t n, const int64_t* idx1, int64_t n1, const int64_t* idx2, int64_t n2,
+                              uint8_t* mask, void* stream) {
+  if (!h) return PINN_EINVAL;
+  if (n <= 0 || n1 < 0 || n2 < 0 || !mask || (n1 > 0 && !idx1) || (n2 > 0 && !idx2) || ((uintptr_t)mask & 3u))
+    return fail(h, PINN_EINVAL, "pinn_mask_from_index_sets: bad argument (mask must be 4-byte aligned with room for n rounded up to 4)");
+  DevGuard dev_guard(h->device);
+  CU(h, launch_mask_from_index_sets(reinterpret_cast<const long long*>(idx1), n1, reinterpret_cast<const long long*>(idx2), n2,
+                                    mask, n, (cudaStream_t)stream));
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->launches += 1;
+  return 0;
 }
 
 int pinn_fields(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z, const void* R,
@@ -576,12 +620,18 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n, const void* x
     if (nchunk > 1) CU(h, cudaEventRecord(h->ev_chunk[c], sc));
   }
   if (zero_copy) {
-    int rc = loss_fwd_bwd_impl(h, variant, n, mapped[0], mapped[1], mapped[2], mapped[3], in_dtype, (const uint8_t*)mapped[4],
-                               th_dev, wdev, th_inl, w_inl, grad_mask, bcutoff, outp, outp + 8, edev, st);
+    LossCall c;
+    c.variant = variant; c.n = n; c.x = mapped[0]; c.y = mapped[1]; c.z = mapped[2]; c.R = mapped[3]; c.in_dtype = in_dtype;
+    c.mask = (const uint8_t*)mapped[4]; c.theta = th_dev; c.weights = wdev; c.theta_inline = th_inl; c.weights_inline = w_inl;
+    c.grad_mask = grad_mask; c.bcutoff = bcutoff; c.sums = outp; c.dtheta = outp + 8; c.E_out = edev;
+    int rc = loss_fwd_bwd_impl(h, c, st);
     if (rc) return rc;
   } else if (nchunk == 1) {
-    int rc = loss_fwd_bwd_impl(h, variant, n, base, base + col, base + 2 * col, base + 3 * col, in_dtype, mdev, th_dev, wdev,
-                               th_inl, w_inl, grad_mask, bcutoff, outp, outp + 8, edev, st);
+    LossCall c;
+    c.variant = variant; c.n = n; c.x = base; c.y = base + col; c.z = base + 2 * col; c.R = base + 3 * col; c.in_dtype = in_dtype;
+    c.mask = mdev; c.theta = th_dev; c.weights = wdev; c.theta_inline = th_inl; c.weights_inline = w_inl;
+    c.grad_mask = grad_mask; c.bcutoff = bcutoff; c.sums = outp; c.dtheta = outp + 8; c.E_out = edev;
+    int rc = loss_fwd_bwd_impl(h, c, st);
     if (rc) return rc;
   } else {
     std::lock_guard<std::mutex> lk(h->mu);

@@ -32,7 +32,8 @@ struct alignas(128) Wts {
   float WgL[12], bgL[12], wg[12];        // 10 used
   float bo, bE, bg, pad0;
   float w0s[NH], w1s[NH], b1s[NH], b2s[NH];  // w0, w1, b1, b2 times -log2(e): pre-activations arrive as the MUFU.EX2 argument
-  float pad1[24];                        // keeps the operand images below 128-byte aligned
+  float WE1s[NE], bE1s[NE], bE2s[NE];    // the same for the E-net ...
+  float WgLs[12], bgLs[12];              // ... and the gate (10 used); 480 floats so far: the images below stay 128-byte aligned
   // ---- tcgen05 B operands (pinn_step_tc.cu): [hi | lo] TF32 split, K-major canonical no-swizzle layout
   //      (8-row x 16-byte core matrices; see umma_off()) ----
   float BS[2][NH * NH];                  // n = j        : W2[j][k]                      (A = s)
@@ -54,6 +55,22 @@ __host__ __device__ constexpr int umma_off(int n, int k, int N) {
 }
 static_assert(sizeof(Wts) % 16 == 0, "Wts must be a multiple of 16 bytes for cp.async.bulk");
 static_assert(offsetof(Wts, BS) % 128 == 0 && offsetof(Wts, W2) % 16 == 0, "operand images must stay aligned");
+
+// entry i of the canonical theta -> index inside ITS tensor when that tensor is stored in train.py's (in,out) layout
+// (x @ A + b, train.py:4-5) instead of nn.Linear's (out,in); only W1 (16,2), W2 (16,16) and WE2 (32,32) differ
+__host__ __device__ constexpr int in_out_index(int tensor, int j) {
+  return tensor == 0 ? (j % 2) * NH + j / 2 : tensor == 2 ? (j % NH) * NH + j / NH : tensor == 8 ? (j % NE) * NE + j / NE : j;
+}
+// tensor index k (state_dict order) and start offset of entry i of theta - compare/select chains on immediates (an
+// offset table indexed at run time would live on the thread's stack)
+__host__ __device__ inline void theta_locate(int i, int& k, int& off) {
+  k = 0; off = O_W1;
+#define PINN_T(K, O) if (i >= (O)) { k = (K); off = (O); }
+  PINN_T(1, O_B1) PINN_T(2, O_W2) PINN_T(3, O_B2) PINN_T(4, O_WO) PINN_T(5, O_BO) PINN_T(6, O_WE1) PINN_T(7, O_BE1)
+  PINN_T(8, O_WE2) PINN_T(9, O_BE2) PINN_T(10, O_WE) PINN_T(11, O_BE) PINN_T(12, O_WGL) PINN_T(13, O_BGL) PINN_T(14, O_WG)
+  PINN_T(15, O_BG)
+#undef PINN_T
+}
 
 struct VariantCoef {  // res = cL*lap(psi) + cV*(1/r1+1/r2)*psi + cE*E*psi ; N = sN * sum(evals) + bo
   float sN, cL, cV, cE;

@@ -250,12 +250,16 @@ __device__ __forceinline__ void build_weight_image(const float* __restrict__ th,
   for (int i = t; i < NE; i += nt) {
     out->WE1[i] = th[O_WE1 + i]; out->bE1[i] = th[O_BE1 + i];
     out->bE2[i] = th[O_BE2 + i]; out->wE[i] = th[O_WE + i];
+    out->WE1s[i] = th[O_WE1 + i] * NEG_LOG2E; out->bE1s[i] = th[O_BE1 + i] * NEG_LOG2E;
+    out->bE2s[i] = th[O_BE2 + i] * NEG_LOG2E;
   }
   for (int i = t; i < 12; i += nt) {
     const bool in = i < NL;
     out->WgL[i] = in ? th[O_WGL + i] : 0.0f;
     out->bgL[i] = in ? th[O_BGL + i] : 0.0f;
     out->wg[i] = in ? th[O_WG + i] : 0.0f;
+    out->WgLs[i] = in ? th[O_WGL + i] * NEG_LOG2E : 0.0f;
+    out->bgLs[i] = in ? th[O_BGL + i] * NEG_LOG2E : 0.0f;
   }
   if (t == 0) { out->bo = th[O_BO]; out->bE = th[O_BE]; out->bg = th[O_BG]; out->pad0 = 0.0f; }
   if (FULL) {
@@ -325,6 +329,9 @@ __device__ __forceinline__ float2 sigm2_pre(const float2 up) {
   const float2 d = __fadd2_rn(make_float2(ex2_approx(up.x), ex2_approx(up.y)), make_float2(1.0f, 1.0f));
   return make_float2(rcp_approx(d.x), rcp_approx(d.y));
 }
+
+// one sigmoid whose argument already carries the factor -log2(e)
+__device__ __forceinline__ float sigm_pre(float up) { return rcp_approx(1.0f + ex2_approx(up)); }
 
 #define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
 #define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))

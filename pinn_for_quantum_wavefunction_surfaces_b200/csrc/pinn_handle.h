@@ -80,16 +80,34 @@ struct DevGuard {
   DevGuard& operator=(const DevGuard&) = delete;
 };
 
-// The training evaluation behind pinn_loss_fwd_bwd / pinn_loss_fwd_bwd_host / the trainer (pinn_capi.cu).
-// theta / weights: device pointers, or NULL with theta_inline / weights_inline = HOST arrays that travel inside the
-// kernel parameters (tcgen05 engine).  adam (optional): optimizer step fused behind the reduction (the trainer).
-// presample (optional): the trainer's next batch drawn by extra blocks of the reduction kernel.
+// The training evaluation behind pinn_loss_fwd_bwd[_tensors] / pinn_loss_fwd_bwd_host / the trainer (pinn_capi.cu).
 namespace pinn { struct AdamParams; struct SampleParams; }
-int loss_fwd_bwd_impl(pinn_handle* h, int variant, int64_t n, const void* x, const void* y, const void* z, const void* R,
-                      int in_dtype, const uint8_t* mask, const float* theta, const double* weights, const float* theta_inline,
-                      const double* weights_inline, uint32_t grad_mask, float bcutoff, double* sums, double* dtheta,
-                      float* E_out, cudaStream_t st, const pinn::AdamParams* adam = nullptr,
-                      unsigned long long* adam_ticket = nullptr, const pinn::SampleParams* presample = nullptr);
+struct LossCall {
+  int variant = 0;
+  int64_t n = 0;
+  const void *x = nullptr, *y = nullptr, *z = nullptr, *R = nullptr;  // device (or mapped page-locked host) columns
+  int in_dtype = PINN_F32;
+  const uint8_t* mask = nullptr;
+  // theta: exactly one of - packed float32 device vector; HOST float32[1521] that travels inside the kernel parameters;
+  // the caller's 16 tensors (device pointers in canonical order, float32/float64, (out,in) or train.py (in,out) layout)
+  const float* theta = nullptr;
+  const float* theta_inline = nullptr;
+  const void* const* theta_tensors = nullptr;
+  int tensors_f64 = 0, tensors_in_out = 0;
+  // loss weights: device pointer, or HOST double[3] carried by value, or neither (sets counted on the device first)
+  const double* weights = nullptr;
+  const double* weights_inline = nullptr;
+  uint32_t grad_mask = 0xFFFFu;
+  float bcutoff = 17.5f;
+  double *sums = nullptr, *dtheta = nullptr;
+  void* E_out = nullptr;
+  int E_f64 = 0;          // E_out is float64
+  int dtheta_in_out = 0;  // 2-D tensors of dtheta in train.py's (in,out) layout
+  const pinn::AdamParams* adam = nullptr;       // optimizer step fused behind the reduction (the trainer)
+  unsigned long long* adam_ticket = nullptr;
+  const pinn::SampleParams* presample = nullptr;  // the trainer's next batch drawn by extra blocks of the reduction kernel
+};
+int loss_fwd_bwd_impl(pinn_handle* h, const LossCall& c, cudaStream_t st);
 
 // The workspace of stream `st` with room for at least `rows` partial rows (created / grown on first use; the handle mutex
 // is held by the caller).  NULL + error message on failure.

@@ -34,10 +34,17 @@ struct StepParams {
   VariantCoef vc;
   int base_grads, gate_grads;  // reverse sweeps wanted (fine-tune mode clears both)
   GridDesc grid;
-  // HOST pointers, read by the launchers only (tcgen05 engine, *_host entry): when set, theta (1521 float) and the three
-  // loss weights travel inside the kernel parameters instead of through a preceding host-to-device copy
+  // HOST pointers, read by the launchers only: when set, theta (1521 float; the *_host entry) and / or the three loss
+  // weights travel inside the kernel parameters instead of through a preceding host-to-device copy
   const float* theta_inline;
   const double* weights_inline;
+  int w_by_value;         // set by the launcher: the loss weights are in the parameter block behind this struct
+  // the caller's 16 parameter tensors instead of a packed vector (pinn_loss_fwd_bwd_tensors): device pointers in
+  // canonical (state_dict) order, float32 or float64, nn.Linear (out,in) or train.py (in,out) layout; every CTA gathers
+  // them while it builds its operand images - no packing kernel, no packed copy in front of the launch
+  const void* theta_tensors[16];
+  int theta_from_tensors, tensors_f64, tensors_in_out;
+  int E_f64;              // E_out points at float64 (the reference's dtype) instead of float32
 };
 
 // Launch as a programmatic dependent of the kernel in front of it in the stream: the grid may be set up (and, where
@@ -93,9 +100,13 @@ struct DpArgs {
 // presample (optional): extra blocks of the same launch draw the trainer's next batch (pinn_sample.cuh)
 struct AdamParams;
 struct SampleParams;
+// E_f64: E_out holds float64; dtheta_in_out: the 2-D tensors of dtheta are written in train.py's (in,out) layout
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
                           cudaStream_t st, const AdamParams* adam = nullptr, unsigned long long* adam_ticket = nullptr,
-                          const SampleParams* presample = nullptr);
+                          const SampleParams* presample = nullptr, int E_f64 = 0, int dtheta_in_out = 0);
+// boundary index sets (int64 row indices, device) -> per-point mask bytes (bit 0: set 1, bit 1: set 2); mask 4-byte aligned
+cudaError_t launch_mask_from_index_sets(const long long* idx1, long long n1, const long long* idx2, long long n2, uint8_t* mask,
+                                        long long n, cudaStream_t st);
 
 }  // namespace pinn

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
                                                               uint32_t grad_mask,
                                                               double* __restrict__ dtheta, double* __restrict__ sums,
                                                               const float* __restrict__ E_out, long long n, const DpArgs dp,
-                                                              const AdamFuse ad, const SampleFuse sf) {
+                                                              const AdamFuse ad, const SampleFuse sf, const int E_f64,
+                                                              const int dtheta_in_out) {
   if (blockIdx.x >= DP_BLOCKS) {
     // sampler blocks: they touch nothing the step kernel in front reads or writes (other batch buffer), so they do not
     // wait for it; the reduction blocks below do, which also keeps this grid from completing early
@@ -157,12 +158,11 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
     tot[e] = t;
     if (idx < NTHETA) {
       // tensor index of this scalar -> honour grad_mask
-      const int offs[17] = {O_W1, O_B1, O_W2, O_B2, O_WO, O_BO, O_WE1, O_BE1, O_WE2, O_BE2, O_WE, O_BE,
-                            O_WGL, O_BGL, O_WG, O_BG, NTHETA};
-      int ti = 0;
-#pragma unroll
-      for (int k = 1; k < 16; k++) ti += (idx >= offs[k]);
-      dtheta[idx] = ((grad_mask >> ti) & 1u) ? t : 0.0;
+      int ti, off;
+      theta_locate(idx, ti, off);
+      // the caller's layout: nn.Linear (out,in) = canonical, or train.py's (in,out) for the 2-D tensors
+      const int dst = dtheta_in_out ? off + in_out_index(ti, idx - off) : idx;
+      dtheta[dst] = ((grad_mask >> ti) & 1u) ? t : 0.0;
     }
   }
   __syncthreads();
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
     const double Lpde = w0 * r2, Lbc = w1 * p1 + w2 * p2;
     sums[0] = Lpde + Lbc; sums[1] = Lpde; sums[2] = Lbc; sums[3] = sE;
     sums[4] = r2; sums[5] = p1; sums[6] = p2;
-    sums[7] = (E_out && n > 0) ? (double)E_out[n - 1] : 0.0;
+    sums[7] = (E_out && n > 0) ? (E_f64 ? reinterpret_cast<const double*>(E_out)[n - 1] : (double)E_out[n - 1]) : 0.0;
   }
   if (!ad.on) return;
 
@@ -268,7 +268,7 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 cudaError_t launch_reduce(const double* partials, int nrows, const double* weights, const double* weights_inline,
                           uint32_t grad_mask, double* dtheta, double* sums, const float* E_out, long long n, const DpArgs& dp,
                           cudaStream_t st, const AdamParams* adam, unsigned long long* adam_ticket,
-                          const SampleParams* presample) {
+                          const SampleParams* presample, int E_f64, int dtheta_in_out) {
   AdamFuse ad{};
   if (adam) { ad.on = 1; ad.a = *adam; ad.ticket = adam_ticket; }
   SampleFuse sf{};
@@ -276,7 +276,33 @@ cudaError_t launch_reduce(const double* partials, int nrows, const double* weigh
   RedWeights wi{};
   if (weights_inline) { wi.w[0] = weights_inline[0]; wi.w[1] = weights_inline[1]; wi.w[2] = weights_inline[2]; wi.use = 1; }
   return launch_pdl(reduce_partials_kernel, dim3(DP_BLOCKS + (presample ? PRESAMPLE_BLOCKS : 0)), dim3(RED_SLICES * 32), 0, st,
-                    partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp, ad, sf);
+                    partials, nrows, weights, wi, grad_mask, dtheta, sums, E_out, n, dp, ad, sf, E_f64, dtheta_in_out);
+}
+
+// Boundary index sets -> mask bytes.  The reference hands LossFunctions the two sets as index tensors
+// (torch.where(r >= BCcutoff), poc/main.py:392-393; train.py:38-39); the step kernel wants one byte per point.  One
+// launch for both sets: bits are OR-ed into the aligned 32-bit word that holds the byte (a point may be in both sets).
+__global__ void __launch_bounds__(256) mask_from_index_sets_kernel(const long long* __restrict__ idx1, long long n1,
+                                                                 const long long* __restrict__ idx2, long long n2,
+                                                                 unsigned int* __restrict__ mask_words, long long n) {
+  const long long tot = n1 + n2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const bool second = i >= n1;
+    const long long row = second ? idx2[i - n1] : idx1[i];
+    if (row < 0 || row >= n) continue;  // (the reference would raise an IndexError; out-of-range rows are ignored here)
+    atomicOr(&mask_words[row >> 2], (second ? 2u : 1u) << (8u * (unsigned)(row & 3)));
+  }
+}
+cudaError_t launch_mask_from_index_sets(const long long* idx1, long long n1, const long long* idx2, long long n2, uint8_t* mask,
+                                        long long n, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(mask, 0, (size_t)((n + 3) / 4) * 4, st);
+  if (e != cudaSuccess) return e;
+  const long long tot = n1 + n2;
+  if (tot <= 0) return cudaSuccess;
+  long long blocks = (tot + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  mask_from_index_sets_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx1, n1, idx2, n2, reinterpret_cast<unsigned int*>(mask), n);
+  return cudaGetLastError();
 }
 
 }  // namespace pinn

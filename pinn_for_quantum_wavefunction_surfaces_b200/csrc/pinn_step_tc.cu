@@ -99,6 +99,30 @@ __device__ __forceinline__ void coord_stage_issue(const StepParams& p, unsigned 
   // the aligned 4-byte word that holds mask[i] (allocations are at least 4-byte granular); the reader picks the byte
   if (p.mask) cp_async4(b + 4 * COORD_COL_BYTES + slot * 4, (const void*)((uintptr_t)(p.mask + i) & ~(uintptr_t)3));
 }
+// Full super-tiles of 16-byte aligned columns travel as FIVE bulk copies (cp.async.bulk, the TMA engine) issued by one
+// thread: 512 B (float32) or 1 KB (float64) per column plus 128 mask bytes, completing on the stage's mbarrier.  Over
+// PCIe (page-locked host inputs read in place) the bus then sees a few large reads per super-tile instead of the 16 + 4
+// 128-byte requests of the per-lane path, which all 148 CTAs used to issue in bursts at their tile boundaries; the
+// per-lane path remains for the ragged last super-tile and for unaligned columns.
+__device__ __forceinline__ void coord_stage_issue_bulk(const StepParams& p, unsigned char* buf, uint64_t* bar, long long st) {
+  const uint32_t b = smem_u32(buf), mb = smem_u32(bar);
+  const uint32_t colb = p.in_f64 ? 1024u : 512u;
+  const uint32_t total = 4u * colb + (p.mask ? 128u : 0u);
+  // the buffer was last READ through the generic proxy (by every warp, two super-tiles ago; ordered before this point
+  // by the role / group barriers): order those reads before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(total) : "memory");
+  const char* src[4] = {(const char*)p.x, (const char*)p.y, (const char*)p.z, (const char*)p.R};
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(b + c * COORD_COL_BYTES),
+                 "l"(src[c] + (size_t)st * colb), "r"(colb), "r"(mb)
+                 : "memory");
+  if (p.mask)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(b + 4 * COORD_COL_BYTES),
+                 "l"(p.mask + (size_t)st * 128), "r"(128u), "r"(mb)
+                 : "memory");
+}
 __device__ __forceinline__ RawPt coord_stage_read(const StepParams& p, const unsigned char* buf, int slot) {
   RawPt r;
   if (p.in_f64) {
@@ -460,11 +484,13 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
     float e1[16];
 #pragma unroll
     for (int k4 = 0; k4 < 16; k4 += 4) {
-      const float4 wv = LD4(&w.WE1[k16 + k4]), bv = LD4(&w.bE1[k16 + k4]);
-      e1[k4 + 0] = sigm(fmaf(R, wv.x, bv.x));
-      e1[k4 + 1] = sigm(fmaf(R, wv.y, bv.y));
-      e1[k4 + 2] = sigm(fmaf(R, wv.z, bv.z));
-      e1[k4 + 3] = sigm(fmaf(R, wv.w, bv.w));
+      // pre-activations arrive as the MUFU.EX2 argument (weights pre-multiplied by -log2 e): one rounding in front of the
+      // exponential instead of two, like the MLP roles
+      const float4 wv = LD4(&w.WE1s[k16 + k4]), bv = LD4(&w.bE1s[k16 + k4]);
+      e1[k4 + 0] = sigm_pre(fmaf(R, wv.x, bv.x));
+      e1[k4 + 1] = sigm_pre(fmaf(R, wv.y, bv.y));
+      e1[k4 + 2] = sigm_pre(fmaf(R, wv.z, bv.z));
+      e1[k4 + 3] = sigm_pre(fmaf(R, wv.w, bv.w));
       if (STASH) ST4(&E1row[(k16 + k4) ^ sx], e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
     }
     tc_st_split16<true>(t0 + E_A_HI + k16, t0 + E_A_LO + k16, e1);
@@ -493,12 +519,12 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
     tc_wait_ld(v);
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 b2v = LD4(&w.bE2[j16 + j4]), wEv = LD4(&w.wE[j16 + j4]);
+      const float4 b2v = LD4(&w.bE2s[j16 + j4]), wEv = LD4(&w.wE[j16 + j4]);
       const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
       float e2[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        e2[i] = sigm(v[j4 + i] + b2a[i]);
+        e2[i] = sigm_pre(fmaf(v[j4 + i], NEG_LOG2E, b2a[i]));
         E = fmaf(wEa[i], e2[i], E);
       }
       if (STASH) ST4(&Vrow[(j16 + j4) ^ sx], e2[0], e2[1], e2[2], e2[3]);
@@ -510,7 +536,7 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
 __device__ __forceinline__ float tc_gate_forward(const Wts& w, float R) {
   float g = w.bg;
 #pragma unroll
-  for (int i = 0; i < NL; i++) g = fmaf(w.wg[i], sigm(fmaf(R, w.WgL[i], w.bgL[i])), g);
+  for (int i = 0; i < NL; i++) g = fmaf(w.wg[i], sigm_pre(fmaf(R, w.WgLs[i], w.bgLs[i])), g);
   return g;
 }
 
@@ -609,7 +635,7 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
     float ch[32];
 #pragma unroll
     for (int i = 0; i < NL; i++) {
-      const float s = sigm(fmaf(R, w.WgL[i], w.bgL[i]));
+      const float s = sigm_pre(fmaf(R, w.WgLs[i], w.bgLs[i]));
       const float ub = gate_grads ? gbar * w.wg[i] * fmaf(-s, s, s) : 0.0f;
       ch[i] = ub * R;
       ch[10 + i] = ub;
@@ -655,6 +681,7 @@ static_assert(128 * TC_REG_ENET + 256 * TC_REG_MLP <= 384 * 168, "register rebal
 
 struct TcParamsPlain {
   StepParams p;
+  double w[4];  // loss weights by value when p.w_by_value
 };
 struct TcParamsInline {
   StepParams p;
@@ -671,6 +698,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   Wts& w = *reinterpret_cast<Wts*>(smem_raw);  // only the first WTS_TC_BYTES are staged / valid
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw + WTS_TC_BYTES);  // [0]: weight copy, [1..3]: roles
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + WTS_TC_BYTES + 32);
+  uint64_t* cfull = reinterpret_cast<uint64_t*>(smem_raw + WTS_TC_BYTES + 40);  // [COORD_STAGES]: bulk coordinate copies landed
   float2* mbox = reinterpret_cast<float2*>(smem_raw + WTS_TC_BYTES + 64);
   float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
   unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - COORD_STAGES * COORD_STAGE_BYTES;
@@ -690,6 +718,8 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   if (tid == 32) {
 #pragma unroll
     for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbars[i])));
+#pragma unroll
+    for (int i = 0; i < COORD_STAGES; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cfull[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -700,7 +730,14 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   pdl_wait();
   const int slot = grp * 32 + lane;
   const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
-  if (stager) {
+  // training launches with 16-byte aligned columns move their full super-tiles as bulk copies (one issuing thread)
+  const bool cbulk = TRAIN && COORD_AHEAD == 1 && !p.grid.on &&
+                     ((((uintptr_t)p.x | (uintptr_t)p.y | (uintptr_t)p.z | (uintptr_t)p.R | (uintptr_t)p.mask) & 15u) == 0);
+  auto tile_bulk = [&](long long st) { return cbulk && (st * 128 + 128 <= p.n); };
+  const bool bulk_issuer = stager && grp == 0 && lane == 0;
+  if (stager && tile_bulk(blockIdx.x)) {
+    if (bulk_issuer) coord_stage_issue_bulk(p, cstage, &cfull[0], blockIdx.x);
+  } else if (stager) {
     const long long i0 = (long long)blockIdx.x * 128 + slot;
     coord_stage_issue(p, cstage, slot, i0 < p.n ? i0 : p.n - 1);
     cp_async_commit();
@@ -726,6 +763,17 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         const float4 v = src[j];
         const float val = lane == 0 ? v.x : lane == 1 ? v.y : lane == 2 ? v.z : v.w;
         if (lane < 4 && 4 * j + lane < NTHETA) th_s[4 * j + lane] = val;
+      }
+    } else if (p.theta_from_tensors) {
+      // the caller's 16 tensors (float32 / float64, (out,in) or train.py's (in,out) layout): gathered here, converted
+      // to float32 like `theta.float()` would
+      for (int i = tid; i < NTHETA; i += blockDim.x) {
+        int k, off;
+        theta_locate(i, k, off);
+        int j = i - off;
+        if (p.tensors_in_out) j = in_out_index(k, j);
+        th_s[i] = p.tensors_f64 ? (float)static_cast<const double*>(p.theta_tensors[k])[j]
+                                : static_cast<const float*>(p.theta_tensors[k])[j];
       }
     } else if (bulk_ok) {
       if (tid == 32) {
@@ -769,7 +817,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
 
     double wpde = 0.0, wbc1 = 0.0, wbc2 = 0.0;
     if (TRAIN) {
-      if constexpr (INLINE) { wpde = q.w[0]; wbc1 = q.w[1]; wbc2 = q.w[2]; }
+      if (INLINE || p.w_by_value) { wpde = q.w[0]; wbc1 = q.w[1]; wbc2 = q.w[2]; }
       else { wpde = p.weights[0]; wbc1 = p.weights[1]; wbc2 = p.weights[2]; }
     }
     const float w_pde = (float)wpde, w_bc1 = (float)wbc1, w_bc2 = (float)wbc2;
@@ -801,13 +849,25 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       TL(0);
       if (it < 38) TLK(2 + it);
       const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
+      const bool this_bulk = tile_bulk(st);
+      if (this_bulk) mbar_wait(smem_u32(&cfull[it % COORD_STAGES]), (uint32_t)(it / COORD_STAGES) & 1u);
       const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
       const Geom g = geom_from_raw(raw);
       const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
       if (stager) {  // coordinates COORD_AHEAD super-tiles ahead: in flight while this one (and the next) is computed
         const long long in = pidx + (long long)COORD_AHEAD * gridDim.x * 128;
-        if (st + (long long)COORD_AHEAD * gridDim.x < nsuper)
-          coord_stage_issue(p, cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES, slot, in < p.n ? in : p.n - 1);
+        const long long stn = st + (long long)COORD_AHEAD * gridDim.x;
+        if (stn < nsuper) {
+          unsigned char* nbuf = cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES;
+          if (tile_bulk(stn)) {
+            // (training launches only.)  The target buffer was read at the top of the previous super-tile; this thread
+            // has since passed the E-net role barrier of that tile's reverse sweep, which every E-net warp reaches after
+            // its group's mid-tile barrier, i.e. after all 12 warps had read their coordinates.
+            if (bulk_issuer) coord_stage_issue_bulk(p, nbuf, &cfull[(it + COORD_AHEAD) % COORD_STAGES], stn);
+          } else {
+            coord_stage_issue(p, nbuf, slot, in < p.n ? in : p.n - 1);
+          }
+        }
         cp_async_commit();
       }
       float2* box = gbox + (it & 1) * (3 * 32);
@@ -877,7 +937,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
               p.hpsi[pidx] = fmaf(gate, fmaf(-0.5f, DN, -q * N),
                                   fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1)));
           } else if (!IS_MLP) {
-            if (p.E_out) p.E_out[pidx] = E;
+            if (p.E_out) { if (p.E_f64) reinterpret_cast<double*>(p.E_out)[pidx] = (double)E; else p.E_out[pidx] = E; }
           }
         }
         continue;
@@ -886,7 +946,8 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
       float m1f, m2f;
       if (p.mask) {
-        const unsigned mk = *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
+        const unsigned mk = this_bulk ? (unsigned)cbuf[4 * COORD_COL_BYTES + slot]   // bulk: the 128 mask bytes as they lie
+                                      : *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
         m1f = (mk & 1u) ? 1.0f : 0.0f;
         m2f = (mk & 2u) ? 1.0f : 0.0f;
       } else {
@@ -917,7 +978,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
           tc_mlp_extras_only(Hs, lane, extra, acc);
         }
       } else {
-        if (valid && p.E_out) p.E_out[pidx] = E;
+        if (valid && p.E_out) { if (p.E_f64) reinterpret_cast<double*>(p.E_out)[pidx] = (double)E; else p.E_out[pidx] = E; }
         const float gbar = fmaf(rbar, fmaf(cE * E, N, inner), pbar * N);
         const float Ebar = rbar * cE * psi;
         tc_enet_backward(w, c, g.R, Ebar, gbar, p.gate_grads != 0, Hs, Gs, lane, acc);
@@ -1049,10 +1110,14 @@ static cudaError_t launch_step_tc_t(const StepParams& p, int grid, cudaStream_t 
     q.theta[NTHETA] = q.theta[NTHETA + 1] = q.theta[NTHETA + 2] = 0.0f;
     q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0.0;
     if (p.weights_inline) memcpy(q.w, p.weights_inline, 3 * sizeof(double));
+    q.p.w_by_value = p.weights_inline != nullptr;
     return launch_pdl(kern, dim3(grid), dim3((NEV + 1) * 128), smem, st, q);
   } else {
     TcParamsPlain q;
     q.p = p;
+    q.w[0] = q.w[1] = q.w[2] = q.w[3] = 0.0;
+    if (p.weights_inline) memcpy(q.w, p.weights_inline, 3 * sizeof(double));
+    q.p.w_by_value = p.weights_inline != nullptr;
     return launch_pdl(kern, dim3(grid), dim3((NEV + 1) * 128), smem, st, q);
   }
 }

@@ -85,6 +85,52 @@ __global__ void enet_curve_kernel(const float* __restrict__ th, const double* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Roofline denominator, measured where and when the benchmark runs: a register-resident FFMA loop (16 independent
+// accumulators per thread, 256 threads x 8 blocks per SM - the loop of tools/microbench/pipes.cu that reaches the
+// FP32 pipe's rate).  bench.py reports the kernel against THIS number (MEASURED_PEAKS.json has no FP32 entry).
+// ---------------------------------------------------------------------------------------------
+constexpr int FFMA_PEAK_ITERS = 4096, FFMA_PEAK_ACC = 16;
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, float b, float c) {
+  float a[FFMA_PEAK_ACC];
+#pragma unroll
+  for (int i = 0; i < FFMA_PEAK_ACC; i++) a[i] = 0.5f + 0.001f * i + threadIdx.x;
+  for (int it = 0; it < FFMA_PEAK_ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < FFMA_PEAK_ACC; i++) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < FFMA_PEAK_ACC; i++) s += a[i];
+  if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the loop alive without traffic
+}
+cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, double* ms_best) {
+  float* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, (size_t)sm_count * 8 * 256 * sizeof(float));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const dim3 grid(sm_count * 8), block(256);
+  for (int i = 0; i < 3; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f);
+  float best = 1e30f;
+  for (int r = 0; r < 5 && e == cudaSuccess; r++) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 4; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f);
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    ms /= 4.0f;
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess) return e;
+  *ms_best = best;
+  *fma_per_s = (double)FFMA_PEAK_ITERS * FFMA_PEAK_ACC * 256.0 * 8.0 * sm_count / (best * 1e-3);
+  return cudaSuccess;
+}
+
 cudaError_t launch_enet_curve(const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
                               cudaStream_t st) {
   enet_curve_kernel<<<(n + 127) / 128, 128, 0, st>>>(theta, R, n, E, dE, d2E, gate);

@@ -74,9 +74,12 @@ static int trainer_enqueue(pinn_trainer* t, bool sample_now, bool presample_next
   SampleParams next{};
   if (presample_next) next = sampler_params(t, b ^ 1);
   // the optimizer step (and the next batch) ride in the reduction kernel: two launches per step
-  int rc = loss_fwd_bwd_impl(h, c.variant, c.n, t->x[b], t->y[b], t->z[b], t->R[b], PINN_F32, t->mask[b], t->theta32,
-                             t->weights[b], nullptr, nullptr, c.grad_mask, c.bcutoff, t->sums, t->grad, t->E, st, &a,
-                             t->adam_ticket, presample_next ? &next : nullptr);
+  LossCall lc;
+  lc.variant = c.variant; lc.n = c.n; lc.x = t->x[b]; lc.y = t->y[b]; lc.z = t->z[b]; lc.R = t->R[b]; lc.in_dtype = PINN_F32;
+  lc.mask = t->mask[b]; lc.theta = t->theta32; lc.weights = t->weights[b]; lc.grad_mask = c.grad_mask; lc.bcutoff = c.bcutoff;
+  lc.sums = t->sums; lc.dtheta = t->grad; lc.E_out = t->E; lc.adam = &a; lc.adam_ticket = t->adam_ticket;
+  lc.presample = presample_next ? &next : nullptr;
+  int rc = loss_fwd_bwd_impl(h, lc, st);
   if (rc) return rc;
   return 0;
 }
@@ -139,6 +142,13 @@ int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const do
   a.best_after = (double)best_after; a.grad_mask = grad_mask; a.best_mode = best_mode; a.hist_mean_E = history_mean_E;
   CU(h, launch_adam(a, (cudaStream_t)stream));
   h->launches += 1;
+  return 0;
+}
+
+int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms) {
+  if (!h || !fma_per_s || !ms) return PINN_EINVAL;
+  DevGuard dev_guard(h->device);
+  CU(h, measure_fp32_peak(h->sm_count, h->s_main, fma_per_s, ms));
   return 0;
 }
 

@@ -147,8 +147,56 @@ class HostStep:
         return self.sums, self.dtheta
 
 
+_OFFS = [0, 32, 48, 304, 320, 336, 337, 369, 401, 1425, 1457, 1489, 1490, 1500, 1510, 1520, 1521]  # pinn_theta_offsets
+_SIZES = [_OFFS[i + 1] - _OFFS[i] for i in range(16)]
+_DT = {torch.float32: _F32, torch.float64: _F64}
+
+
+def _rows(ix):
+    """torch.where tuple (poc/main.py:392-393) or 1-D row indices (train.py:38-39) -> the row-index tensor"""
+    return ix[0] if isinstance(ix, (tuple, list)) else ix
+
+
+class _MaskCache:
+    """The mask bytes of the last few (idx1, idx2) pairs.  The reference loops keep a batch - and with it the two index
+    tensors - for many steps (poc/main.py:396: the last 10 % of the epochs; sc_sampling > 1), so the mask of an
+    unchanged pair of index tensors (same storage, same version) is reused instead of rebuilt."""
+
+    def __init__(self, keep=4):
+        self.keep, self.items = keep, []
+
+    def get(self, h, n, r1, r2, dev, stream):
+        key = (n, dev.index, r1.data_ptr(), r1.numel(), r1._version, r2.data_ptr(), r2.numel(), r2._version)
+        for k, m, _ in self.items:
+            if k == key:
+                return m
+        n1, n2 = r1.numel(), r2.numel()
+        if r1.dtype != torch.int64 or not r1.is_contiguous() or r1.device != dev:
+            r1 = r1.to(device=dev, dtype=torch.int64).contiguous()
+        if r2.dtype != torch.int64 or not r2.is_contiguous() or r2.device != dev:
+            r2 = r2.to(device=dev, dtype=torch.int64).contiguous()
+        mask = torch.empty((n + 3) // 4 * 4, dtype=torch.uint8, device=dev)
+        rc = h.L.pinn_mask_from_index_sets(h.h, n, _ptr(r1) if n1 else None, n1, _ptr(r2) if n2 else None, n2, _ptr(mask),
+                                           ctypes.c_void_p(stream))
+        h.check(rc, "pinn_mask_from_index_sets")
+        # the index tensors are kept alive with the entry: a freed tensor's address could otherwise come back with
+        # different content under the same key
+        self.items.insert(0, (key, mask, (r1, r2)))
+        del self.items[self.keep:]
+        return mask
+
+
+_mask_cache = _MaskCache()
+
+
 class _PinnLoss(torch.autograd.Function):
-    """forward(variant, order, x, y, z, R, idx1, idx2, *16 params) -> (Ltot, Lpde, Lbc, E)."""
+    """forward(variant, order, x, y, z, R, idx1, idx2, *16 params) -> (Ltot, Lpde, Lbc, E).
+
+    CUDA tensors: one library call (pinn_loss_fwd_bwd_tensors) on torch's current stream.  The kernel gathers the 16
+    parameter tensors through their pointers (no packing, no dtype conversion in front of the launch), takes the three
+    loss weights by value, writes E in the parameters' dtype and the gradient in the parameters' layout; the only other
+    device work is the mask of the two index sets (one memset + one kernel, cached while the index tensors are unchanged)
+    and, in backward, one multiplication by the upstream gradient.  CPU tensors: pinn_loss_fwd_bwd_host."""
 
     @staticmethod
     def forward(ctx, variant, order, x, y, z, R, idx1, idx2, *params):
@@ -159,24 +207,51 @@ class _PinnLoss(torch.autograd.Function):
         dev = xs.device
         pdt = params[0].dtype
         grad_mask = P.grad_mask_from_requires_grad(params, order)
-        ctx.order, ctx.shapes, ctx.needs = order, [tuple(p.shape) for p in params], [p.requires_grad for p in params]
-        mask, c1, c2 = indices_to_mask(n, idx1, idx2, dev)
-        if c1 == 0 or c2 == 0:
-            # the reference takes the mean of an empty selection -> NaN loss (hard part 6)
-            weights = [1.0 / n, float("inf") if c1 == 0 else 1.0 / c1, float("inf") if c2 == 0 else 1.0 / c2]
-        else:
-            weights = [1.0 / n, 1.0 / c1, 1.0 / c2]
-        pack = P.pack_poc if order == "poc" else P.pack_trainpy
+        ctx.order, ctx.shapes, ctx.needs = order, [p.shape for p in params], [p.requires_grad for p in params]
+        r1, r2 = _rows(idx1), _rows(idx2)
+        c1, c2 = r1.numel(), r2.numel()
+        # the reference takes the mean of an empty selection -> NaN loss (hard part 6): weight inf
+        weights = (1.0 / n, 1.0 / c1 if c1 else float("inf"), 1.0 / c2 if c2 else float("inf"))
         if dev.type == "cuda":
-            theta = pack(params, dtype=torch.float32, device=dev)
-            wdev = torch.tensor(weights, dtype=torch.float64, device=dev)
-            sums, dtheta, E = loss_and_grad_raw(variant, xs, ys, zs, Rs, theta, mask, wdev, grad_mask, True)
+            h = Handle.get(dev.index if dev.index is not None else torch.cuda.current_device())
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            mask = _mask_cache.get(h, n, r1, r2, dev, stream)
+            if ys.dtype != xs.dtype or zs.dtype != xs.dtype or Rs.dtype != xs.dtype:
+                raise ValueError("x, y, z, R must share one dtype")
+            direct = pdt in _DT and all(p.dtype == pdt and p.is_cuda and p.is_contiguous() for p in params)
+            out = torch.empty(8 + P.N_THETA, dtype=torch.float64, device=dev)
+            E = torch.empty(n, dtype=pdt if pdt in _DT else torch.float32, device=dev)
+            w = (ctypes.c_double * 3)(*weights)
+            if direct:
+                ptrs = (ctypes.c_void_p * 16)(*[p.data_ptr() for p in params])
+                rc = h.L.pinn_loss_fwd_bwd_tensors(h.h, int(variant), n, xs.data_ptr(), ys.data_ptr(), zs.data_ptr(),
+                                                   Rs.data_ptr(), _DT[xs.dtype], mask.data_ptr(), ptrs, _DT[pdt],
+                                                   VARIANT_POC if order == "poc" else VARIANT_TRAINPY, w, int(grad_mask),
+                                                   BC_CUTOFF, out.data_ptr(), out.data_ptr() + 64, E.data_ptr(), _DT[E.dtype],
+                                                   stream)
+                h.check(rc, "pinn_loss_fwd_bwd_tensors")
+                ctx.native_layout = True
+            else:  # mixed dtypes / non-contiguous parameters: pack first
+                pack = P.pack_poc if order == "poc" else P.pack_trainpy
+                theta = pack(params, dtype=torch.float32, device=dev)
+                wdev = torch.tensor(weights, dtype=torch.float64, device=dev)
+                E = E.float() if E.dtype != torch.float32 else E
+                loss_and_grad_raw(variant, xs, ys, zs, Rs, theta, mask, wdev, grad_mask, sums=out[:8], dtheta=out[8:], E_out=E)
+                ctx.native_layout = False
+            sums, dtheta = out[:8], out[8:]
         else:
+            mask, _, _ = indices_to_mask(n, idx1, idx2, dev)
+            pack = P.pack_poc if order == "poc" else P.pack_trainpy
             theta64 = pack(params, dtype=torch.float64).contiguous()
-            sums, dtheta, E = _host_step(variant, xs, ys, zs, Rs, theta64, mask, weights, grad_mask, True, BC_CUTOFF)
+            sums, dtheta, E = _host_step(variant, xs, ys, zs, Rs, theta64, mask, list(weights), grad_mask, True, BC_CUTOFF)
+            ctx.native_layout = False
         ctx.save_for_backward(dtheta)
-        Ltot, Lpde, Lbc = sums[0].to(pdt), sums[1].to(pdt), sums[2].to(pdt)
-        E = E.to(pdt).reshape(n, 1)
+        Ltot, Lpde, Lbc = sums[0], sums[1], sums[2]
+        if pdt != torch.float64:
+            Ltot, Lpde, Lbc = Ltot.to(pdt), Lpde.to(pdt), Lbc.to(pdt)
+        if E.dtype != pdt:
+            E = E.to(pdt)
+        E = E.view(n, 1)
         ctx.mark_non_differentiable(Lpde, Lbc, E)
         return Ltot, Lpde, Lbc, E
 
@@ -184,11 +259,20 @@ class _PinnLoss(torch.autograd.Function):
     def backward(ctx, gLtot, gLpde, gLbc, gE):
         (dtheta,) = ctx.saved_tensors
         g = dtheta * gLtot.to(dtheta.dtype)
+        outs = [None] * 8
+        if ctx.native_layout:  # tensors in canonical order, each already in the parameter's own layout: views only
+            parts = g.split(_SIZES)     # one call -> 16 views
+            for k, (shp, need) in enumerate(zip(ctx.shapes, ctx.needs)):
+                if not need:
+                    outs.append(None)
+                    continue
+                part = parts[k if ctx.order == "poc" else P.TRAINPY_TO_POC[k]]
+                outs.append(part if len(shp) == 1 else part.view(shp))
+            return tuple(outs)
         parts = P.unpack_poc(g) if ctx.order == "poc" else P.unpack_trainpy(g)
-        outs = []
         for part, shp, need in zip(parts, ctx.shapes, ctx.needs):
             outs.append(part.reshape(shp) if need else None)
-        return (None,) * 8 + tuple(outs)
+        return tuple(outs)
 
 
 class PinnLossPoc:
@@ -209,7 +293,13 @@ class PinnLossTrainPy:
 
 def loss_poc(model, x, y, z, R, bIndex1, bIndex2):
     """Ltot, LossPDE, Lbc, E for an ``NN_ion``-like module (16 parameters in state_dict order)."""
-    return PinnLossPoc.apply(x, y, z, R, bIndex1, bIndex2, *list(model.parameters()))
+    # the parameter list of a module is walked once and kept with it (a module that gains or loses parameters, or is
+    # moved with .to()/.double() - which replaces the Parameter objects' data in place - keeps the same objects)
+    ps = model.__dict__.get("_pinn_parameters")
+    if ps is None or len(ps) != 16 or next(model.parameters()) is not ps[0]:
+        ps = tuple(model.parameters())
+        model.__dict__["_pinn_parameters"] = ps
+    return _PinnLoss.apply(VARIANT_POC, "poc", x, y, z, R, bIndex1, bIndex2, *ps)
 
 
 def loss_trainpy(x, y, z, R, i1, i2, *params):

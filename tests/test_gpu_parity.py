@@ -330,6 +330,115 @@ def test_trainpy_function_cpu_tensors(init_theta):
     assert tp[0].grad.shape == (2, 16) and tp[2].grad.shape == (16, 16)
 
 
+@pytest.mark.parametrize("order", ["poc", "trainpy"])
+@pytest.mark.parametrize("pdt", [torch.float64, torch.float32])
+def test_tensor_pointer_entry_equals_packed_entry(init_theta, order, pdt):
+    """pinn_loss_fwd_bwd_tensors (the kernel gathers the caller's 16 tensors through their pointers, takes the weights by
+    value, writes E in the parameter dtype and the gradient in the parameter layout) == pinn_loss_fwd_bwd on the packed
+    float32 vector: the same bits."""
+    import ctypes
+    variant = 0 if order == "poc" else 1
+    n = 5000
+    a32, m1, m2 = sample(variant, n, 17)
+    d = dev()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    th = init_theta if pdt == torch.float64 else init_theta.astype(np.float32).astype(np.float64)
+    parts = layout.unpack_poc(th) if order == "poc" else layout.to_trainpy(th)
+    params = [torch.tensor(np.ascontiguousarray(a), dtype=pdt, device=d) for a in parts]
+    mk = t((m1 + 2 * m2).astype(np.uint8))
+    w = [1.0 / n, 1.0 / m1.sum(), 1.0 / m2.sum()]
+    cols = [t(a) for a in a32]
+    s0, g0, E0 = pk.loss_and_grad_raw(variant, *cols, t(th.astype(np.float32)), mk, torch.tensor(w, dtype=torch.float64, device=d),
+                                      want_E=True)
+    h = pk.Handle.get(0)
+    out = torch.empty(8 + 1521, dtype=torch.float64, device=d)
+    E1 = torch.empty(n, dtype=pdt, device=d)
+    ptrs = (ctypes.c_void_p * 16)(*[p.data_ptr() for p in params])
+    code = {torch.float32: 0, torch.float64: 1}
+    rc = h.L.pinn_loss_fwd_bwd_tensors(h.h, variant, n, *[c.data_ptr() for c in cols], 0, mk.data_ptr(), ptrs, code[pdt], variant,
+                                       (ctypes.c_double * 3)(*w), 0xFFFF, 17.5, out.data_ptr(), out.data_ptr() + 64, E1.data_ptr(),
+                                       code[pdt], torch.cuda.current_stream().cuda_stream)
+    h.check(rc, "pinn_loss_fwd_bwd_tensors")
+    torch.cuda.synchronize()
+    assert torch.equal(out[:8], s0) and torch.equal(E1.float(), E0)
+    g1 = out[8:].cpu().numpy()
+    if order == "trainpy":   # canonical tensor order, each tensor in (in,out) layout -> back to (out,in)
+        back = []
+        for i, (nm, shp) in enumerate(layout.POC_TENSORS):
+            blk = g1[OFFS[i]:OFFS[i + 1]]
+            back.append(blk.reshape(shp[::-1]).T.ravel() if len(shp) == 2 else blk)
+        g1 = np.concatenate(back)
+    assert np.array_equal(g1, g0.cpu().numpy())
+
+
+def test_mask_from_index_sets_and_its_cache():
+    n = 10007
+    rng = np.random.default_rng(5)
+    i1 = torch.tensor(np.sort(rng.choice(n, 4000, replace=False)), device=dev())
+    i2 = torch.tensor(np.sort(rng.choice(n, 5000, replace=False)), device=dev())
+    ref, c1, c2 = pk.indices_to_mask(n, (i1, torch.zeros_like(i1)), i2, dev())
+    h = pk.Handle.get(0)
+    st = torch.cuda.current_stream().cuda_stream
+    got = pk.ops._mask_cache.get(h, n, i1, i2, dev(), st)[:n]
+    assert torch.equal(got, ref) and (c1, c2) == (4000, 5000)
+    again = pk.ops._mask_cache.get(h, n, i1, i2, dev(), st)
+    assert again.data_ptr() == got.data_ptr()                       # unchanged index tensors: reused
+    i1[5:] = torch.flip(i1[5:], [0])                                 # an in-place edit bumps the tensor's version
+    fresh = pk.ops._mask_cache.get(h, n, i1, i2, dev(), st)
+    assert fresh.data_ptr() != got.data_ptr()
+    assert torch.equal(fresh[:n], pk.indices_to_mask(n, i1, i2, dev())[0])
+    empty = torch.empty(0, dtype=torch.long, device=dev())
+    m = pk.ops._mask_cache.get(h, 5, empty, torch.tensor([4], device=dev()), dev(), st)[:5]
+    assert m.tolist() == [0, 0, 0, 0, 2]
+
+
+def test_trainpy_function_cuda_tensors(init_theta):
+    """PinnLossTrainPy.apply on CUDA float64 tensors: the direct-pointer path with train.py's order and (in,out) layout."""
+    tp = [torch.tensor(a, device=dev(), requires_grad=True) for a in layout.to_trainpy(init_theta)]
+    a32, m1, m2 = sample(1, 2500, 61)
+    x, y, z, R = [torch.tensor(a.astype(np.float64), device=dev()).reshape(-1, 1) for a in a32]
+    i1, i2 = torch.tensor(np.nonzero(m1)[0], device=dev()), torch.tensor(np.nonzero(m2)[0], device=dev())
+    Ltot, Lpde, Lbc, e = pk.loss_trainpy(x, y, z, R, i1, i2, *tp)
+    (3.0 * Ltot).backward()
+    ref = oracle(1, init_theta, a32, m1, m2)
+    assert Ltot.dtype == torch.float64 and e.dtype == torch.float64 and e.shape == (2500, 1)
+    assert abs(Ltot.item() - ref["Ltot"]) / ref["Ltot"] < 1e-5
+    assert abs(torch.mean(e).item() - ref["E"].mean()) < 1e-5
+    got = layout.from_trainpy([p.grad.cpu().numpy() / 3.0 for p in tp])
+    check_tensors(got, ref["grad"], 1e-5)
+    assert tp[0].grad.shape == (2, 16) and tp[2].grad.shape == (16, 16)
+    # a frozen tensor gets no gradient and does not disturb the others
+    tp2 = [p.detach().clone().requires_grad_(k not in (0, 2)) for k, p in enumerate(tp)]
+    L2 = pk.loss_trainpy(x, y, z, R, i1, i2, *tp2)[0]
+    L2.backward()
+    assert tp2[0].grad is None and tp2[2].grad is None and torch.allclose(tp2[1].grad * 3.0, tp[1].grad, rtol=1e-12)
+
+
+def test_calls_on_different_streams_of_one_handle_do_not_share_scratch(init_theta):
+    """Every stream that calls in gets its own workspace (per-CTA partial rows, set counters): evaluations enqueued on two
+    streams at once - they do overlap on the device - return what they return alone."""
+    d = dev()
+    th = torch.from_numpy(init_theta.astype(np.float32)).to(d)
+    jobs = []
+    for k, n in enumerate((1 << 17, 50000, 1 << 16, 77777)):
+        a32, m1, m2 = sample(0, n, 200 + k)
+        jobs.append([torch.from_numpy(a).to(d) for a in a32])
+    alone = []
+    for cols in jobs:
+        s, g, _ = pk.loss_and_grad_raw(0, *cols, th)          # weights = None: the set-count kernels use the workspace too
+        alone.append((s.clone(), g.clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in jobs]
+    for rep in range(5):
+        res = []
+        for cols, st in zip(jobs, streams):
+            with torch.cuda.stream(st):
+                res.append(pk.loss_and_grad_raw(0, *cols, th))
+        torch.cuda.synchronize()
+        for (s, g, _), (s0, g0) in zip(res, alone):
+            assert torch.equal(s[:7], s0[:7]) and torch.equal(g, g0)
+
+
 def test_empty_boundary_set_gives_nan_like_the_reference(init_theta):
     """mean over an empty selection is NaN in the reference (poc/main.py:349-350); same here."""
     tp = [torch.tensor(a, requires_grad=True) for a in layout.to_trainpy(init_theta)]

@@ -175,7 +175,19 @@ def test_trainer_fine_tune_mask_and_resume(ck):
         b = pk.sample(4096, 12345, t)
         tr3.set_batch(b["x"], b["y"], b["z"], b["R"], b["mask"], b["weights"].cpu().numpy())
         tr3.run(1, resample=False, use_graph=False)
-    assert np.allclose(tr3.read()["theta"], r["theta"], rtol=1e-12, atol=1e-15)
+    r3 = tr3.read()
+    assert np.allclose(r3["theta"], r["theta"], rtol=1e-12, atol=1e-15)
+    # the resumed run keeps its own history (row 0 = first step after the resume) and its own best-model record
+    assert r3["steps"] == 4 and r3["history"].shape == (2, 4) and np.allclose(r3["history"], r["history"][2:4], rtol=1e-12)
+    assert r3["best_step"] in (2, 3) and r3["best_loss"] == r3["history"][r3["best_step"] - 2, 0]
+    fresh = pk.Trainer("trainpy", 4096, th, history_capacity=4)
+    fresh.load_state(mid["theta"], mid["m"], mid["v"], step=2)
+    r0 = fresh.read()
+    assert np.array_equal(r0["best_theta"], mid["theta"]) and r0["best_step"] == -1 and r0["history"].shape == (0, 4)
+    fresh.run(1)                        # train.py rule: the first step after a (re)start is taken unconditionally
+    r1 = fresh.read()
+    assert r1["best_step"] == 2 and np.array_equal(r1["best_theta"], mid["theta"]) and r1["history"].shape == (1, 4)
+    fresh.close()
     for t in (tr, tr2, tr3):
         t.close()
 
@@ -191,30 +203,35 @@ def _enet_np(theta, R):
     return e @ P[10][0] + P[11][0]
 
 
-def test_reference_training_run_with_fused_loss_matches_golden_model(golden_dir):
-    """BASELINE north star: trained E(R) within 1e-4 Hartree of the reference run.  The reference's own loop
-    (restated in oracle/train_loop.py, pinned to the real script on the CPU) is driven with the CUDA op instead of
-    lines 41-57; same torch RNG stream, same Adam, float64 parameters on the host."""
-    tr = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e40.json")))
-    params, trace, hist = tl.trainpy_run(pk.loss_trainpy, n=4096, epochs=40)
+@pytest.mark.parametrize("epochs", [40, 200])
+def test_reference_training_run_with_fused_loss_matches_golden_model(golden_dir, epochs):
+    """BASELINE north star: trained E(R) within 1e-4 Hartree of the reference run; BASELINE config 1 is this run at
+    n = 4096, 200 epochs.  The reference's own loop (restated in oracle/train_loop.py, pinned to the real script on the CPU at
+    both lengths) is driven with the CUDA op instead of lines 41-57; same torch RNG stream, same Adam, float64 parameters
+    on the host.  Measured on B200 (profiles/r02_a_acceptance.txt): max|dE(R)| 8e-8 Ha and max|dtheta| 7e-7 against the real
+    script's model.bin after 200 epochs; the bars are 10x that, far inside the north star's 1e-4 Ha."""
+    tr = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e%d.json" % epochs)))
+    params, trace, hist = tl.trainpy_run(pk.loss_trainpy, n=4096, epochs=epochs)
     assert trace[0] == tr["trace"][0]                      # identical print at step 0
+    assert len(trace) == len(tr["trace"])
     fa = lambda ln: [float(v) for v in ln.replace("(", " ").replace(")", " ").replace("[", " ").replace("]", " ").split()[1:]]
-    for a, b in zip(trace, tr["trace"]):
-        assert np.allclose(fa(a), fa(b), rtol=2e-2), (a, b)
+    for a, b in zip(trace, tr["trace"]):                   # 3 printed digits: one unit of the last digit is <= 1e-2
+        assert np.allclose(fa(a), fa(b), rtol=1.1e-2), (a, b)
     got = pk.pack_trainpy(params, dtype=torch.float64).numpy()
-    ref = pk.convert.theta_from_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e40.bin"))
+    ref = pk.convert.theta_from_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e%d.bin" % epochs))
     R = np.linspace(0.2, 3.0, 57)
     dE = np.abs(_enet_np(got, R) - _enet_np(ref, R)).max()
-    assert dE < 1e-4, dE
-    assert np.abs(got - ref).max() < 1e-3
+    assert dE < 1e-6, dE
+    assert np.abs(got - ref).max() < 1e-5
 
 
-def test_device_trainer_fed_with_the_reference_points_tracks_the_reference(golden_dir, init_theta):
+@pytest.mark.parametrize("epochs", [40, 200])
+def test_device_trainer_fed_with_the_reference_points_tracks_the_reference(golden_dir, init_theta, epochs):
     """Same run through the device-resident trainer (fused Adam, float64 state on the GPU): the host only supplies the
     reference's batches (torch RNG, train.py:26-39)."""
     torch.manual_seed(12345)
     tl.trainpy_run  # the parameter draw consumes the generator first, exactly as in the script
-    n, epochs = 4096, 40
+    n = 4096
     dtype = torch.double
     shapes = [(2, 16), (16,), (16, 16), (16,), (16, 1), (1,), (1, 10), (10,), (10, 1), (1,), (1, 32), (32,), (32, 32), (32,),
               (32, 1), (1,)]
@@ -240,14 +257,16 @@ def test_device_trainer_fed_with_the_reference_points_tracks_the_reference(golde
         tr.run(1, resample=False, use_graph=(tt > 0))
     r = tr.read()
     tr.close()
-    gt = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e40.json")))["trace"]
+    gt = json.load(open(os.path.join(golden_dir, "trainpy_trace_n4096_e%d.json" % epochs)))["trace"]
     for k, ln in enumerate(gt):
         vals = [float(v) for v in ln.replace("(", " ").replace(")", " ").replace("[", " ").replace("]", " ").split()[1:]]
-        assert np.allclose(r["history"][10 * k], vals[:4], rtol=3e-2), (k, r["history"][10 * k], vals)
-    ref = pk.convert.theta_from_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e40.bin"))
+        assert np.allclose(r["history"][10 * k], vals[:4], rtol=1.1e-2), (k, r["history"][10 * k], vals)
+    ref = pk.convert.theta_from_model_bin(os.path.join(golden_dir, "trainpy_model_n4096_e%d.bin" % epochs))
     Rg = np.linspace(0.2, 3.0, 57)
-    assert np.abs(_enet_np(r["best_theta"], Rg) - _enet_np(ref, Rg)).max() < 1e-4
-    assert abs(r["best_loss"] - 7.18217e-06) / 7.18217e-06 < 2e-2
+    # measured 8e-8 Ha after 200 epochs (profiles/r02_a_acceptance.txt); the north star asks for 1e-4
+    assert np.abs(_enet_np(r["best_theta"], Rg) - _enet_np(ref, Rg)).max() < 1e-6
+    best_ref = {40: 7.18217e-06, 200: 1.00569e-06}[epochs]      # last [Lbest] of the real script's trace
+    assert abs(r["best_loss"] - best_ref) / best_ref < 1e-4
 
 
 def test_train_drivers_reduce_the_loss(init_theta):
@@ -290,6 +309,22 @@ def test_grid_energies_vs_oracle(n, rule, ck):
         assert abs(Eint - ref["psiHpsi"] / ref["psi2"]) < 2e-5 * abs(Eint) and abs(Enet - f["E"][-1]) < 1e-6
         assert abs(pk.analysis.energy_from_psi_LCAO(th32, Ri, prm, rule=rule) - ref["lcaoHlcao"] / ref["lcao2"]) < 1e-5
         assert abs(pk.analysis.dEdR_int(th32, Ri, prm, rule=rule) - (ref["dVdR_psi2"] / ref["psi2"] - 0.5 / Ri ** 2)) < 1e-4
+
+
+def test_grid_point_on_a_nucleus_gives_nan_like_the_reference(ck):
+    """Odd n_test puts x = y = z = 0 ... on the grid; with R a multiple of the spacing a grid point sits ON a nucleus, where the
+    reference divides by r = 0 without a guard (poc/main.py:111-120, 442-454): its E_integral is NaN, its E_net is fine
+    (measured with the real code: n_test = 13, R = 3.0 -> (nan, -0.67800954); n_test = 13, R = 2.0 -> -0.76864690).
+    The quadrature kernel does the same - NaN sums, never a silently skipped point - and E_net stays exact."""
+    th = ck["ionHsym_fineTune"]
+    Eint, Enet = pk.analysis.energy_from_psi(th, 3.0, {"n_test": 13})
+    assert np.isnan(Eint) and abs(Enet - (-0.67800954)) < 1e-6
+    s = pk.analysis.grid_sums(th, 3.0, {"n_test": 13})
+    # (the kernel forms r = q * rsqrt(q), which is NaN at q = 0, so psi itself is NaN at that one point and every sum is;
+    # the reference's psi is finite there and only its H psi is not - E_integral is NaN either way)
+    assert np.isnan(s["psiHpsi"]) and np.isnan(s["dVdR_psi2"]) and np.isfinite(s["E_net"])
+    Eint, Enet = pk.analysis.energy_from_psi(th, 2.0, {"n_test": 13}, rule="simpson")   # off the nuclei: the reference's number
+    assert abs(Eint - (-0.7686469036652853)) < 2e-5 and abs(Enet - (-0.79302316)) < 1e-6
 
 
 def test_grid_at_reference_resolution_and_10_8_points(ck):

@@ -274,8 +274,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     prints one JSON line with the keys the driver reads."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    # the way the driver launches it for N > 1: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers - the arm
+    # must still use every host core it may (round 1 ran single-threaded there and inflated the N >= 2 ratios 8.5x)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                        "--points", "8192"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(r.stdout.strip().splitlines()) == 1, r.stdout  # ONE line on stdout
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -286,6 +289,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["vs_baseline"] is None and line["config"]["workload"].startswith("ionHsym")
+    assert line["steps"] == 3                                      # --steps is honoured
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) == line["config"]["host_threads"]
+    assert line["config"]["points_per_gpu"] == 8192 and "full batch" in line["cpu_baseline"]["sample"]
+    # ranks other than 0 exit 0 without work or output
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
 
 
 def test_stash_swizzle_is_conflict_free_for_all_three_access_patterns():
@@ -373,3 +383,25 @@ def test_bench_roofline_denominators():
     assert tc["unit"] == "TFLOP/s" and abs(tc["achieved"] - 27044.0 * n / (ms * 1e-3) / 1e12) < 1e-9
     assert 200.0 < tc["peak"] < 400.0 and abs(tc["frac"] - tc["achieved"] / tc["peak"]) < 1e-12
     assert "measured" in hb["peak_source"] or "fallback" in hb["peak_source"]
+
+
+def test_bench_withholds_ncu_figures_of_another_build(tmp_path, monkeypatch):
+    """roofline.traffic / pipe utilisation are copied from the committed ncu capture only while the kernel sources are the
+    ones it was captured from (profiles/traffic.json: kernel_source_sha256)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    now = bench.kernel_source_sha256()
+    assert len(now) == 64
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "kernel_source_sha256", lambda: now)
+    assert bench.committed_ncu_figures()[:2] == (None, None)
+    body = {"dram_bytes_per_launch": 4300000, "ncu_pipe_utilisation_pct": {"fma": 20.0}, "source": "x", "kernel_source_sha256": now}
+    (prof / "traffic.json").write_text(json.dumps(body))
+    t, pipes, src = bench.committed_ncu_figures()
+    assert t == 4300000 and pipes == {"fma": 20.0} and now[:12] in src
+    body["kernel_source_sha256"] = "0" * 64
+    (prof / "traffic.json").write_text(json.dumps(body))
+    t, pipes, src = bench.committed_ncu_figures()
+    assert t is None and pipes is None and src.startswith("stale")

@@ -12,7 +12,8 @@ variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 finetune = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 dev = torch.device("cuda:0")
-pk.Handle.get(0).set_engine(engine)
+if engine != "tcgen05":  # "ffma": A/B build only (PINN_B200_LIBRARY=tools/dbg/libpinn_b200_ab.so)
+    pk.Handle.get(0).set_engine(engine)
 n = 1 << 18
 g = torch.Generator().manual_seed(5)
 x, y, z, R, i1, i2 = ra.sample_box(n, "poc" if variant == 0 else "trainpy", g)
