@@ -452,6 +452,8 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host buffers of this rank (page-locked batches of the e2e leg) are allocated on the NUMA node of its GPU
+    numa_cpus = pk.bind_host_to_device_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.points
@@ -527,13 +529,20 @@ def main():
         sampler.start()
     # the clock sampler needs ~0.15 s to deliver its first rows: the GPU keeps stepping meanwhile (more warm-up) instead of
     # idling, so that the timed region starts on a busy, clocked-up device straight after the fence
+    # (the number of these steps must be the same on every rank - each one is an exchange - so it is agreed on first)
     t_spin = time.time()
     i_spin = W
-    while time.time() - t_spin < 0.25:
-        for _ in range(20):
-            step(i_spin)
-            i_spin += 1
-        torch.cuda.synchronize()
+    for _ in range(20):
+        step(i_spin)
+        i_spin += 1
+    torch.cuda.synchronize()
+    more = torch.tensor([int(0.25 / max(time.time() - t_spin, 1e-4)) * 20], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(more, op=dist.ReduceOp.MAX)
+    for _ in range(min(int(more.item()), 20000)):
+        step(i_spin)
+        i_spin += 1
+    torch.cuda.synchronize()
     # Two back-to-back timed regions of the same K steps (clocks sampled over both): the first without any extra stream
     # operation gives `value`; the second brackets every step-kernel launch with CUDA events on the launching stream
     # (pinn_profile_begin/collect) and gives the kernel's average duration for the roofline.  (The event records sit
@@ -547,7 +556,8 @@ def main():
     ms_profiled = timed(step, i_spin + K, K)
     kern_ms, kern_n = h.profile_collect()
     # the roofline's denominator, measured now on this device (clock samples of the same window)
-    fp32_peak, fp32_ms = h.measure_fp32_peak()
+    step_mhz = h.step_kernel_clock(torch.cuda.current_stream(dev).cuda_stream)   # CTA 0's own cycles / nanoseconds, last step
+    fp32_peak, fp32_ms, fp32_mhz = h.measure_fp32_peak()
     steady = None
     if not args.no_extras:
         Ks = max(K, 1000)
@@ -572,6 +582,7 @@ def main():
                 dist.all_reduce(out)
 
         Ke = max(3, min(K, 200))
+        fence()
         for i in range(N_BATCHES + 3):   # one pass over every page-locked batch buffer first (the GPU's first touch of a
             e2e_step(i)                  # host page is slower), then the timed calls
         fence()
@@ -598,6 +609,26 @@ def main():
                    "(cp.async.bulk) of the next super-tile's columns over PCIe while the current one is computed; pageable "
                    "inputs are staged in up to 4 chunks)"}
         del host_steps
+        # What the host link gives when all ranks pull their batches at once (plain cudaMemcpyAsync from the same page-locked
+        # buffers, no kernel): the ceiling of the e2e path's scaling.  4.2 MB per step and GPU cross PCIe; on an HGX box
+        # the GPUs share switch uplinks, so the aggregate stops growing long before 8 x the single-GPU rate.
+        fence()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for rep in range(3):
+            for hb, db in zip(host_batches, dev_batches):
+                db.copy_(hb, non_blocking=True)
+        c1.record()
+        fence()
+        gbs = torch.tensor([3 * N_BATCHES * 16.0 * n / (c0.elapsed_time(c1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        gmin, gsum = gbs.clone(), gbs.clone()
+        if world > 1:
+            dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(gsum, op=dist.ReduceOp.SUM)
+        line_extra["e2e"]["host_link_probe"] = {
+            "h2d_GBps_per_gpu_min": float(gmin.item()), "h2d_GBps_all_gpus": float(gsum.item()),
+            "e2e_needs_GBps_per_gpu_at_device_rate": 16.0 * n / (ms / K * 1e-3) / 1e9,
+            "what": "all ranks copy their page-locked batches host->device at once (cudaMemcpyAsync, no kernel)"}
 
         # ---- BASELINE config 4 as written: 2^22 points per step of the whole job, sharded over the ranks
         G = args.global_points
@@ -606,6 +637,7 @@ def main():
         _, db4, w4 = make_batches(n4, nb4, 7000)
         # (make_batches -> dp.global_weights: the weights of a sharded batch are those of the GLOBAL batch)
         step4 = make_step(db4, w4)
+        fence()                      # the ranks drew their batches on the host at different speeds: meet before exchanging
         for i in range(3):
             step4(i)
         K4 = max(3, min(K, 200))
@@ -620,6 +652,7 @@ def main():
         # ---- the whole training loop on the device (sampler -> loss/gradient -> Adam, CUDA-graph replay)
         if world == 1 or fused:
             tr = pk.Trainer("poc", n, load_theta(), seed=1, lr=1e-6, device=local)
+            fence()
             Kl = max(10, min(K, 300))
             ts = torch.cuda.ExternalStream(tr.h.L.pinn_trainer_stream(tr.t), device=dev)
             res = {}
@@ -664,6 +697,7 @@ def main():
                        "points_per_gpu": n, "global_points": int(total_points), "weights": "models/ionHsym.pt (tests/golden/checkpoints.npz)",
                        "inputs": "%d rotating batches resident in HBM, %.0f MB > 126 MB L2" % (N_BATCHES, N_BATCHES * n * 16 / 1e6),
                        "warmup_note": "%d warm-up steps, then %d more untimed steps while the clock sampler starts (no idle gap in front of the timed region)" % (W, i_spin - W),
+                       "host_numa_binding": ("rank 0 bound to CPUs %s-%s of its GPU's NUMA node" % (numa_cpus[0], numa_cpus[-1])) if numa_cpus else "none",
                        "parallelism": ("dp%d point sharding; sum of 1529 f64 over ranks %s" % (
                            world, "fused into the reduction kernel (NVLink peer stores + flags, pinn_dp_*)" if fused
                            else "by one NCCL all-reduce per step")) if world > 1 else "single GPU"},
@@ -674,6 +708,10 @@ def main():
                                         "FFMA loop, %.3f ms per timed kernel, clocks in `clocks`); MEASURED_PEAKS.json has no FP32 entry; "
                                         "round-1 figure of the same loop: %.1f" % (fp32_ms, FP32_PEAK_FALLBACK / 1e12),
                          "flop_per_point": FLOP_PER_POINT,
+                         # the SM clock each kernel actually ran at (block 0 times itself: clock64 / %globaltimer): the step
+                         # kernel keeps the tensor pipe busy and runs below the clock the FFMA loop (and nvidia-smi) see
+                         "effective_sm_mhz": {"step_kernel": round(step_mhz, 1), "ffma_peak_loop": round(fp32_mhz, 1)},
+                         "frac_at_the_step_kernels_own_clock": achieved / (fp32_peak * step_mhz / fp32_mhz) if fp32_mhz > 0 and step_mhz > 0 else None,
                          "kernel": "pinn_step_tc_kernel<2,true,false>",
                          "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "traffic": traffic,
                          "algorithmic_bytes_per_launch": 16 * n, "ncu_pipe_utilisation_pct": ncu_pipes, "ncu_source": ncu_src,

@@ -85,8 +85,13 @@ int pinn_get_engine(pinn_handle* h);
 
 /* Measurement helper (bench.py's roofline denominator): the FP32 FFMA rate of this device right now, from a
  * register-resident loop of independent FFMA chains (best of 5 timings of ~0.3 ms each, CUDA events).
- * fma_per_s: fused multiply-adds per second (x2 = FLOP/s); ms: duration of one timed kernel.  Synchronous. */
-int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms);
+ * fma_per_s: fused multiply-adds per second (x2 = FLOP/s); ms: duration of one timed kernel; sm_mhz: the SM clock the
+ * loop ran at (block 0 times itself with clock64 and %globaltimer).  Synchronous. */
+int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms, double* sm_mhz);
+/* Effective SM clock of the last training evaluation enqueued on `stream`: CTA 0 of the step kernel times itself (SM
+ * cycles and nanoseconds from its entry to the end of its tile loop).  sm_mhz above is the same measurement for the FFMA
+ * loop.  Synchronises the stream. */
+int pinn_step_kernel_clock(pinn_handle* h, void* stream, double* cycles, double* ns);
 
 /* Host-side wall-clock split of the last pinn_loss_fwd_bwd_host call on this handle, microseconds:
  * {enqueue (argument checks, parameter conversion, launches), wait for the device, copy-out, total}. */
@@ -210,7 +215,7 @@ int pinn_loss_fwd_bwd_host(pinn_handle* h, int variant, int64_t n,
  * over the ranks with the same protocol, and every rank's Adam sees the same global gradient (identical replicas).
  * Connect the exchange BEFORE creating the trainer (the peers' addresses are captured in its CUDA graphs).
  * pinn_dp_connect* enable the exchange; pinn_dp_enable switches it off/on; pinn_dp_status returns PINN_ETIMEDOUT if a
- * peer failed to deliver within ~3 s (the kernel then gives up instead of hanging) and the number of completed
+ * peer failed to deliver within ~30 s (the kernel then gives up instead of hanging; every rank stops updating its replica) and the number of completed
  * exchanges; pinn_dp_shutdown (collective by convention: call it on every rank after a barrier) frees the buffer.
  */
 #define PINN_DP_HANDLE_BYTES 64
@@ -220,6 +225,9 @@ int pinn_dp_connect(pinn_handle* h, const void* all_handles);
 int pinn_dp_connect_local(pinn_handle* h, pinn_handle* const* peers);
 int pinn_dp_enable(pinn_handle* h, int on);
 int pinn_dp_status(pinn_handle* h, int64_t* exchanges);
+/* How long a rank polls for its peers before it declares the exchange failed (default ~30 s; call after pinn_dp_init and
+ * before creating trainers / capturing graphs on the handle, which copy the value). */
+int pinn_dp_set_timeout(pinn_handle* h, double seconds);
 int pinn_dp_shutdown(pinn_handle* h);
 
 /* =====================================================================================================

@@ -10,11 +10,11 @@ _LIB_NAME = "libpinn_b200.so"
 EXPORTS = [
     "pinn_version", "pinn_theta_size", "pinn_theta_offsets", "pinn_create", "pinn_destroy", "pinn_last_error",
     "pinn_launch_count", "pinn_set_engine", "pinn_get_engine", "pinn_profile_begin", "pinn_profile_collect", "pinn_loss_fwd_bwd", "pinn_fields", "pinn_loss_fwd_bwd_host",
-    "pinn_loss_fwd_bwd_tensors", "pinn_mask_from_index_sets", "pinn_measure_fp32_peak",
+    "pinn_loss_fwd_bwd_tensors", "pinn_mask_from_index_sets", "pinn_measure_fp32_peak", "pinn_step_kernel_clock",
     "pinn_sample", "pinn_adam_step", "pinn_enet_curve", "pinn_grid_reduce", "pinn_trainer_create", "pinn_trainer_destroy",
     "pinn_trainer_load_state", "pinn_trainer_set_batch", "pinn_trainer_run", "pinn_trainer_read", "pinn_trainer_batch",
     "pinn_trainer_stream",
-    "pinn_host_timing", "pinn_dp_init", "pinn_dp_connect", "pinn_dp_connect_local", "pinn_dp_enable", "pinn_dp_status", "pinn_dp_shutdown",
+    "pinn_host_timing", "pinn_dp_init", "pinn_dp_connect", "pinn_dp_connect_local", "pinn_dp_enable", "pinn_dp_status", "pinn_dp_set_timeout", "pinn_dp_shutdown",
 ]
 
 
@@ -80,8 +80,11 @@ def lib():
         L.pinn_loss_fwd_bwd_tensors.restype = i32
         L.pinn_mask_from_index_sets.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp]
         L.pinn_mask_from_index_sets.restype = i32
-        L.pinn_measure_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.pinn_measure_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                             ctypes.POINTER(ctypes.c_double)]
         L.pinn_measure_fp32_peak.restype = i32
+        L.pinn_step_kernel_clock.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.pinn_step_kernel_clock.restype = i32
         L.pinn_fields.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.pinn_fields.restype = i32
         L.pinn_loss_fwd_bwd_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, u32, f32, vp, vp, vp]
@@ -125,10 +128,40 @@ def lib():
         L.pinn_dp_enable.restype = i32
         L.pinn_dp_status.argtypes = [vp, ctypes.POINTER(i64)]
         L.pinn_dp_status.restype = i32
+        L.pinn_dp_set_timeout.argtypes = [vp, ctypes.c_double]
+        L.pinn_dp_set_timeout.restype = i32
         L.pinn_dp_shutdown.argtypes = [vp]
         L.pinn_dp_shutdown.restype = i32
         _lib = L
         return L
+
+
+def bind_host_to_device_numa(device=0):
+    """Pin the calling process to the CPUs that are local to CUDA device `device` (its PCIe root's NUMA node, read from
+    /sys/bus/pci/devices/<id>/local_cpulist).  Host buffers allocated and page-locked AFTERWARDS land on that node, so the
+    kernels of the *_host entry read them over the device's own PCIe root instead of across the socket interconnect - which
+    is what limits 8 ranks streaming their batches at once.  Returns the CPU set, or None when the topology is unknown."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(int(device))
+        busid = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % busid) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):   # no driver / no sysfs entry: leave the affinity alone
+        return None
 
 
 class Handle:
@@ -171,10 +204,16 @@ class Handle:
         return {v: k for k, v in self.ENGINES.items()}[int(self.L.pinn_get_engine(self.h))]
 
     def measure_fp32_peak(self):
-        """-> (FLOP/s of the FP32 FFMA pipe measured now on this device, milliseconds of one timed kernel)"""
-        r, ms = ctypes.c_double(), ctypes.c_double()
-        self.check(self.L.pinn_measure_fp32_peak(self.h, ctypes.byref(r), ctypes.byref(ms)), "pinn_measure_fp32_peak")
-        return 2.0 * r.value, ms.value
+        """-> (FLOP/s of the FP32 FFMA pipe measured now on this device, milliseconds of one timed kernel, SM MHz it ran at)"""
+        r, ms, mhz = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self.check(self.L.pinn_measure_fp32_peak(self.h, ctypes.byref(r), ctypes.byref(ms), ctypes.byref(mhz)), "pinn_measure_fp32_peak")
+        return 2.0 * r.value, ms.value, mhz.value
+
+    def step_kernel_clock(self, stream):
+        """-> effective SM clock (MHz) of the last training evaluation enqueued on `stream` (a cudaStream_t as int)"""
+        c, ns = ctypes.c_double(), ctypes.c_double()
+        self.check(self.L.pinn_step_kernel_clock(self.h, ctypes.c_void_p(stream), ctypes.byref(c), ctypes.byref(ns)), "pinn_step_kernel_clock")
+        return c.value / ns.value * 1e3 if ns.value > 0 else 0.0
 
     def profile_begin(self):
         self.check(self.L.pinn_profile_begin(self.h), "pinn_profile_begin")
@@ -212,6 +251,9 @@ class Handle:
         k = ctypes.c_int64()
         self.check(self.L.pinn_dp_status(self.h, ctypes.byref(k)), "pinn_dp_status")
         return int(k.value)
+
+    def dp_set_timeout(self, seconds):
+        self.check(self.L.pinn_dp_set_timeout(self.h, float(seconds)), "pinn_dp_set_timeout")
 
     def dp_shutdown(self):
         self.check(self.L.pinn_dp_shutdown(self.h), "pinn_dp_shutdown")

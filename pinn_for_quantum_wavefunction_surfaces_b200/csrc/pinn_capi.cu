@@ -325,6 +325,15 @@ int pinn_dp_enable(pinn_handle* h, int on) {
   return 0;
 }
 
+int pinn_dp_set_timeout(pinn_handle* h, double seconds) {
+  if (!h) return PINN_EINVAL;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!(seconds > 0.0) || seconds > 3600.0) return fail(h, PINN_EINVAL, "pinn_dp_set_timeout: need 0 < seconds <= 3600");
+  if (h->dp.world < 1) return fail(h, PINN_EINVAL, "pinn_dp_set_timeout: the exchange is not initialised");
+  h->dp.timeout_cycles = (long long)(seconds * 2.0e9);  // SM cycles at ~2 GHz: a bound, not a stopwatch
+  return 0;
+}
+
 int pinn_dp_status(pinn_handle* h, int64_t* exchanges) {
   if (!h) return PINN_EINVAL;
   std::lock_guard<std::mutex> lk(h->mu);

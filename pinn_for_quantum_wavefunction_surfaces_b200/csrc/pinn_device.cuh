@@ -333,6 +333,13 @@ __device__ __forceinline__ float2 sigm2_pre(const float2 up) {
 // one sigmoid whose argument already carries the factor -log2(e)
 __device__ __forceinline__ float sigm_pre(float up) { return rcp_approx(1.0f + ex2_approx(up)); }
 
+// Q = al11 v1^2 + al12 v1 v2 + al22 v2^2 for two hidden units.  (A 5-operation form v1 (al11 v1 + al12 v2) + al22 v2^2, a
+// packed accumulation of N and D, and a non-volatile mma.sync were measured together in round 2: +0.1 % - inside the
+// noise - and another rounding pattern at the trained weights; not adopted.)
+__device__ __forceinline__ float2 quad_form2(float al11, float al12, float al22, float2 v1, float2 v2) {
+  return f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));
+}
+
 #define LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
 #define ST4(ptr, a, b, c, d) (*reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d))
 

@@ -85,6 +85,10 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 //   ctl  8 x u64 {exchanges completed, blocks done, status, set-count exchanges completed, ...}
 //   cnt  [2 slots][DP_MAX_WORLD][2] x 8 B : the sampler's boundary-set sizes, same {data, step} words (pinn_train.cu)
 constexpr int DP_MAX_WORLD = 8;
+// How long a rank polls for a peer's contribution before it declares the run failed (SM cycles, ~30 s): long enough for any
+// host-side skew between the ranks' launches (one rank writing a checkpoint, drawing a batch on the CPU ...), short
+// enough that a dead peer does not hang the GPU.
+constexpr long long DP_TIMEOUT_CYCLES = 60000000000ll;
 constexpr int DP_BLOCKS = NPART / 32;
 constexpr size_t DP_ROWS_BYTES = 2ull * DP_MAX_WORLD * NPART * 16;
 constexpr size_t DP_CTL_BYTES = 64;
@@ -94,6 +98,7 @@ struct DpArgs {
   int world = 0;  // <= 1: no exchange
   int rank = 0;
   unsigned char* peer[DP_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // exchange buffers, [rank] = own
+  long long timeout_cycles = DP_TIMEOUT_CYCLES;  // pinn_dp_set_timeout
 };
 // weights: device pointer, or NULL with weights_inline (host, 3 double) carried in the kernel parameters
 // adam (optional): the optimizer step of the device-resident trainer fused behind the reduction (pinn_train.h)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
   unsigned int step = 0;
   size_t slot = 0;
   // A peer that never delivers (time-out below) poisons the run: ctl[2] is set and stays set, this and every later
-  // launch then skips the polling (no 3 s stall per step) AND the fused optimizer step, so the parameters stay what they
+  // launch then skips the polling (no 30 s stall per step) AND the fused optimizer step, so the parameters stay what they
   // were before the failed exchange; pinn_dp_status / pinn_trainer_read report PINN_ETIMEDOUT.
   __shared__ volatile int dp_failed_s;
   if (threadIdx.x == 0) dp_failed_s = 0;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
           lo = ld_relaxed_sys_v2(src);
           hi = ld_relaxed_sys_v2(src + 2);
           if (lo.y == step && hi.y == step) { ok = true; break; }
-          if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never arrived; report instead of hanging the GPU
+          if (clock64() - t0 > dp.timeout_cycles) {  // a peer never arrived; report instead of hanging the GPU
             for (int q = 0; q < dp.world; q++)  // tell everybody: the peers stop updating their replicas as well
               st_release_sys(reinterpret_cast<unsigned long long*>(dp.peer[q] + DP_ROWS_BYTES) + 2, 1ull);
             dp_failed_s = 1;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(RED_SLICES * 32) reduce_partials_kernel(const 
               lo = ld_relaxed_sys_v2(src);
               hi = ld_relaxed_sys_v2(src + 2);
               if (lo.y == step && hi.y == step) { ok = true; break; }
-              if (clock64() - t0 > 6000000000ll) {
+              if (clock64() - t0 > dp.timeout_cycles) {
                 for (int q = 0; q < dp.world; q++)
                   st_release_sys(reinterpret_cast<unsigned long long*>(dp.peer[q] + DP_ROWS_BYTES) + 2, 1ull);
                 dp_failed_s = 1;

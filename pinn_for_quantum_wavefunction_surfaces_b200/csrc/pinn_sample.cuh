@@ -53,14 +53,20 @@ __device__ __forceinline__ void sample_finish(const SampleParams& s) {
         st_relaxed_sys_v2(dst + 2, (unsigned int)c2, step);
         const unsigned int* src = reinterpret_cast<const unsigned int*>(own + DP_ROWS_BYTES + DP_CTL_BYTES) + (slot + r) * 4;
         const long long t0 = clock64();
-        uint2 a, b;
-        for (;;) {
+        uint2 a = make_uint2(0u, 0u), b = a;
+        // ctl[2] != 0: an earlier exchange of this run already failed (a peer never delivered) - do not wait again
+        bool failed = ld_acquire_sys(&ctl[2]) != 0ull;
+        while (!failed) {
           a = ld_relaxed_sys_v2(src);
           b = ld_relaxed_sys_v2(src + 2);
           if (a.y == step && b.y == step) break;
-          if (clock64() - t0 > 6000000000ll) { ctl[2] = 1ull; break; }
+          if (clock64() - t0 > dp.timeout_cycles) {
+            for (int q = 0; q < dp.world; q++)  // every rank stops updating its replica (see reduce_partials_kernel)
+              st_release_sys(reinterpret_cast<unsigned long long*>(dp.peer[q] + DP_ROWS_BYTES) + 2, 1ull);
+            failed = true;
+          }
         }
-        c[r][0] = a.x; c[r][1] = b.x;
+        c[r][0] = failed ? 0ull : a.x; c[r][1] = failed ? 0ull : b.x;
       }
     }
     __syncwarp();

@@ -257,8 +257,10 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
         const float2 t = sigm2_pre(f2fma(make_float2(V0[j], V0[j + 1]), f2bc(NEG_LOG2E), make_float2(b2a[i], b2a[i + 1])));
         const float2 tp = f2fma(f2neg(t), t, t);
         const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
-        const float2 Q = f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));
+        const float2 Q = quad_form2(al11, al12, al22, v1, v2);
         const float2 gD = f2fma(tp, v3, f2mul(tpp, Q));
+        // (sequential scalar accumulation: N of the boundary points is one fixed rounding pattern - DESIGN.md section 4 -
+        // and this order is the measured one)
         accN = fmaf(woa[i], t.x, accN); accN = fmaf(woa[i + 1], t.y, accN);
         accD = fmaf(woa[i], gD.x, accD); accD = fmaf(woa[i + 1], gD.y, accD);
         tt[i] = t.x; tt[i + 1] = t.y; va[i] = v1.x; va[i + 1] = v1.y; vb[i] = v2.x; vb[i + 1] = v2.y; vD[i] = v3.x; vD[i + 1] = v3.y;
@@ -319,7 +321,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
         const float2 tp = f2fma(f2neg(t), t, t);
         const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
         const float2 tppp = f2mul(tp, f2fma(f2bc(-6.0f), tp, f2bc(1.0f)));
-        const float2 Q = f2fma(f2mul(f2bc(al11), v1), v1, f2fma(f2mul(f2bc(al12), v1), v2, f2mul(f2mul(f2bc(al22), v2), v2)));
+        const float2 Q = quad_form2(al11, al12, al22, v1, v2);
         const float2 gD = f2fma(tp, v3, f2mul(tpp, Q));
         const float2 tbar = f2mul(f2bc(lamN), wo2), gDbar = f2mul(f2bc(lamD), wo2);
         const float2 dw = f2fma(f2bc(lamN), t, f2mul(f2bc(lamD), gD));
@@ -709,6 +711,17 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   const bool is_mlp = role < NEV;
   const int sx = swz_tc(lane);
   TLK(0);
+  // CTA 0 times itself (SM cycles and nanoseconds, entry to the end of its tile loop): the effective SM clock of the launch,
+  // read back by pinn_step_kernel_clock.  It is lower than the clock nvidia-smi samples while the tensor pipe is in use.
+  // (start values parked in two free slots of the 64-byte barrier block, not in registers that would stay live)
+  uint32_t* clk0_slot = reinterpret_cast<uint32_t*>(smem_raw + WTS_TC_BYTES + 36);
+  unsigned long long* ns0_slot = reinterpret_cast<unsigned long long*>(smem_raw + WTS_TC_BYTES + 56);
+  if (blockIdx.x == 0 && tid == 0) {
+    unsigned long long ns0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    *ns0_slot = ns0;
+    *clk0_slot = (uint32_t)clock();
+  }
 
   // ---- one-time setup: TMEM allocation (warp 0), mbarriers, weight image by TMA bulk copy ----
   if (warp == 0) {
@@ -730,11 +743,15 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   pdl_wait();
   const int slot = grp * 32 + lane;
   const bool stager = !is_mlp && !p.grid.on;  // the E-net warp (the role with slack) moves its group's coordinates
-  // training launches with 16-byte aligned columns move their full super-tiles as bulk copies (one issuing thread)
-  const bool cbulk = TRAIN && COORD_AHEAD == 1 && !p.grid.on &&
+  // The launches of the *_host entry (INLINE: theta and weights in the kernel parameters, coordinates usually page-locked
+  // host memory read in place) move the full super-tiles of 16-byte aligned columns as bulk copies, one issuing thread.
+  // Launches on device-resident batches keep the per-lane cp.async stage and carry no bulk code at all: with it the step on
+  // HBM-resident inputs measured 1.7 % slower (0.1166 vs 0.1146 ms, tools/ab_time.py on one box, whichever warp issues and
+  // whoever waits), against 3 % gained when the coordinates cross PCIe.
+  const bool cbulk = INLINE && TRAIN && COORD_AHEAD == 1 && !p.grid.on &&
                      ((((uintptr_t)p.x | (uintptr_t)p.y | (uintptr_t)p.z | (uintptr_t)p.R | (uintptr_t)p.mask) & 15u) == 0);
-  auto tile_bulk = [&](long long st) { return cbulk && (st * 128 + 128 <= p.n); };
-  const bool bulk_issuer = stager && grp == 0 && lane == 0;
+  auto tile_bulk = [&](long long st) { return INLINE && cbulk && (st * 128 + 128 <= p.n); };
+  const bool bulk_issuer = stager && grp == 3 && lane == 0;
   if (stager && tile_bulk(blockIdx.x)) {
     if (bulk_issuer) coord_stage_issue_bulk(p, cstage, &cfull[0], blockIdx.x);
   } else if (stager) {
@@ -838,7 +855,10 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     // 32 points lie beyond n compute on a clamped index with zero weight
     const long long nsuper = (p.n + 127) >> 7;
     int it = 0;
-    if (stager) cp_async_wait_next();  // the first super-tile's coordinates (requested before the weight image was built)
+    if (stager) {  // the first super-tile's coordinates (requested before the weight image was built)
+      cp_async_wait_next();
+      if (tile_bulk(blockIdx.x)) mbar_wait(smem_u32(&cfull[0]), 0u);
+    }
     __syncthreads();
     TLK(1);
     for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
@@ -849,8 +869,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       TL(0);
       if (it < 38) TLK(2 + it);
       const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
-      const bool this_bulk = tile_bulk(st);
-      if (this_bulk) mbar_wait(smem_u32(&cfull[it % COORD_STAGES]), (uint32_t)(it / COORD_STAGES) & 1u);
+      const bool this_bulk = tile_bulk(st);   // (its arrival was awaited by the E-net warps before the last group barrier)
       const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
       const Geom g = geom_from_raw(raw);
       const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
@@ -889,7 +908,14 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         box[2 * 32 + lane] = make_float2(E, gt);
       }
       TL(5);
-      if (stager) cp_async_wait_next();  // the NEXT tile's coordinates have landed; the barrier publishes them to the group
+      if (stager) {  // the NEXT tile's coordinates have landed; the barrier publishes them to the group
+        cp_async_wait_next();
+        // bulk copies complete on the stage's mbarrier: the E-net warps (the role with slack) wait for it here, off the MLP
+        // warps' critical path, and the group barrier hands the data on (use number (it+1)/2 of that stage -> parity)
+        const long long stn = st + (long long)gridDim.x;
+        if (stn < nsuper && tile_bulk(stn))
+          mbar_wait(smem_u32(&cfull[(it + 1) % COORD_STAGES]), (uint32_t)((it + 1) / COORD_STAGES) & 1u);
+      }
       named_barrier(1 + grp, (NEV + 1) * 32);
       TL(6);
 
@@ -987,6 +1013,13 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     }
 
     TLK(40);
+    if (TRAIN && blockIdx.x == 0 && tid == 0) {  // (tid 0 is an MLP thread of role 0; both branches run this lambda)
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      double* tm = reinterpret_cast<double*>(mbox);  // the mailbox is free after the last super-tile
+      tm[0] = (double)((uint32_t)clock() - *clk0_slot);   // 32-bit cycle counter: differences are exact modulo 2^32
+      tm[1] = (double)(ns1 - *ns0_slot);
+    }
     // the reduction kernel behind this launch may be set up now (it waits for this grid to complete before it reads)
     pdl_launch_dependents();
     // ---- teardown of tensor memory: all tcgen05 traffic of the CTA is complete (every MMA was waited for) ----
@@ -1074,6 +1107,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       else { w0 = 0; w1 = 0; }  // padding
       double sum = 0.0;
       for (int wv = w0; wv < w1; wv++) sum += (double)stash[wv * NPART + i];
+      if (i >= NPART - 2 && blockIdx.x == 0) sum = reinterpret_cast<const double*>(mbox)[i - (NPART - 2)];  // CTA 0's own timing
       row[i] = sum;
     }
     TLK(41);

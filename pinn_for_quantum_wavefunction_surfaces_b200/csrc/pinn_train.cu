@@ -91,7 +91,13 @@ __global__ void enet_curve_kernel(const float* __restrict__ th, const double* __
 // FP32 pipe's rate).  bench.py reports the kernel against THIS number (MEASURED_PEAKS.json has no FP32 entry).
 // ---------------------------------------------------------------------------------------------
 constexpr int FFMA_PEAK_ITERS = 4096, FFMA_PEAK_ACC = 16;
-__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, float b, float c) {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, float b, float c, double* __restrict__ clk) {
+  long long clk0 = 0;
+  unsigned long long ns0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    clk0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+  }
   float a[FFMA_PEAK_ACC];
 #pragma unroll
   for (int i = 0; i < FFMA_PEAK_ACC; i++) a[i] = 0.5f + 0.001f * i + threadIdx.x;
@@ -103,19 +109,26 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out,
 #pragma unroll
   for (int i = 0; i < FFMA_PEAK_ACC; i++) s += a[i];
   if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the loop alive without traffic
+  if (clk && blockIdx.x == 0 && threadIdx.x == 0) {  // block 0 times itself: SM cycles and nanoseconds
+    unsigned long long ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    clk[0] = (double)(clock64() - clk0);
+    clk[1] = (double)(ns1 - ns0);
+  }
 }
-cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, double* ms_best) {
+cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, double* ms_best, double* sm_mhz) {
   float* out = nullptr;
-  cudaError_t e = cudaMalloc(&out, (size_t)sm_count * 8 * 256 * sizeof(float));
+  cudaError_t e = cudaMalloc(&out, (size_t)sm_count * 8 * 256 * sizeof(float) + 2 * sizeof(double));
   if (e != cudaSuccess) return e;
+  double* clk = reinterpret_cast<double*>(out + (size_t)sm_count * 8 * 256);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   const dim3 grid(sm_count * 8), block(256);
-  for (int i = 0; i < 3; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f);
+  for (int i = 0; i < 3; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f, clk);
   float best = 1e30f;
   for (int r = 0; r < 5 && e == cudaSuccess; r++) {
     cudaEventRecord(e0, st);
-    for (int i = 0; i < 4; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f);
+    for (int i = 0; i < 4; i++) ffma_peak_kernel<<<grid, block, 0, st>>>(out, 0.999f, 1e-3f, clk);
     cudaEventRecord(e1, st);
     e = cudaEventSynchronize(e1);
     float ms = 0.0f;
@@ -124,9 +137,12 @@ cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, 
     if (ms < best) best = ms;
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double hclk[2] = {0.0, 1.0};
+  if (e == cudaSuccess) e = cudaMemcpy(hclk, clk, sizeof(hclk), cudaMemcpyDeviceToHost);
   cudaFree(out);
   if (e != cudaSuccess) return e;
   *ms_best = best;
+  *sm_mhz = hclk[1] > 0.0 ? hclk[0] / hclk[1] * 1e3 : 0.0;  // effective SM clock of the last launch (block 0)
   *fma_per_s = (double)FFMA_PEAK_ITERS * FFMA_PEAK_ACC * 256.0 * 8.0 * sm_count / (best * 1e-3);
   return cudaSuccess;
 }

@@ -97,7 +97,7 @@ __device__ inline void adam_bookkeeping(const AdamParams& a, unsigned long long 
   *a.step = t + 1ull;
 }
 
-cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, double* ms_best);
+cudaError_t measure_fp32_peak(int sm_count, cudaStream_t st, double* fma_per_s, double* ms_best, double* sm_mhz);
 cudaError_t launch_enet_curve(const float* theta, const double* R, int n, double* E, double* dE, double* d2E, double* gate,
                               cudaStream_t st);
 

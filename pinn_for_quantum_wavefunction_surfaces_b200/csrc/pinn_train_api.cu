@@ -145,10 +145,29 @@ int pinn_adam_step(pinn_handle* h, double* theta, double* m, double* v, const do
   return 0;
 }
 
-int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms) {
-  if (!h || !fma_per_s || !ms) return PINN_EINVAL;
+int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms, double* sm_mhz) {
+  if (!h || !fma_per_s || !ms || !sm_mhz) return PINN_EINVAL;
   DevGuard dev_guard(h->device);
-  CU(h, measure_fp32_peak(h->sm_count, h->s_main, fma_per_s, ms));
+  CU(h, measure_fp32_peak(h->sm_count, h->s_main, fma_per_s, ms, sm_mhz));
+  return 0;
+}
+
+// Effective SM clock of the LAST training evaluation enqueued on `stream` through this handle: CTA 0 of the step kernel
+// times itself (clock64 and %globaltimer, entry to the end of its tile loop).  Synchronises the stream.
+int pinn_step_kernel_clock(pinn_handle* h, void* stream, double* cycles, double* ns) {
+  if (!h || !cycles || !ns) return PINN_EINVAL;
+  DevGuard dev_guard(h->device);
+  const double* src = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (const pinn_workspace& w : h->ws)
+      if (w.stream == (cudaStream_t)stream && w.partials) src = w.partials + (NPART - 2);
+  }
+  if (!src) return fail(h, PINN_EINVAL, "pinn_step_kernel_clock: no training evaluation has run on this stream");
+  CU(h, cudaStreamSynchronize((cudaStream_t)stream));
+  double v[2];
+  CU(h, cudaMemcpy(v, src, sizeof(v), cudaMemcpyDeviceToHost));
+  *cycles = v[0]; *ns = v[1];
   return 0;
 }
 

@@ -87,9 +87,9 @@ class Trainer:
 
     def __init__(self, variant, n, theta0, seed=12345, lr=8e-3, betas=(0.9, 0.999), eps=1e-8, box=None, cutoff=0.005,
                  bcutoff=17.5, grad_mask=0xFFFF, best_mode=None, best_after=0, sc_sampling=1, freeze_after=INT64_MAX,
-                 history_capacity=0, history_mean_E=None, device=None):
+                 history_capacity=0, history_mean_E=None, device=None, handle=None):
         variant = {"poc": 0, "trainpy": 1}.get(variant, variant)
-        self.h = _handle(device)
+        self.h = handle if handle is not None else _handle(device)   # default: the cached per-device Handle
         if box is None:
             box = BOX_POC if variant == 0 else BOX_TRAINPY
         c = TrainConfig()

@@ -63,6 +63,44 @@ def test_dp_argument_errors():
         h.dp_enable(True)   # not initialised
 
 
+def test_a_peer_that_never_delivers_is_reported_and_stops_the_optimizer(golden_dir):
+    """World of 2 whose second rank never runs (two handles on ONE device suffice: rank 1 stays idle).  Rank 0 polls for
+    the configured time-out, gives up instead of hanging the GPU, and from then on: pinn_dp_status and Trainer.read()
+    report PINN_ETIMEDOUT, later steps return at once (no second wait), and the fused Adam leaves the replica untouched."""
+    import time
+    th = np.load(os.path.join(golden_dir, "trainpy_n2048.npz"))["theta"]
+    h0, h1 = pk.Handle(0), pk.Handle(0)
+    try:
+        h0.dp_init(0, 2, want_ipc=False)
+        h1.dp_init(1, 2, want_ipc=False)
+        h0.dp_connect_local([h0, h1])
+        h1.dp_connect_local([h0, h1])
+        h0.dp_set_timeout(0.25)
+        import ctypes
+        th64 = np.ascontiguousarray(th, np.float64)
+        tr0 = pk.Trainer("poc", 4096, th, seed=3, lr=8e-3, history_capacity=4, handle=h0)
+        t0 = time.time()
+        tr0.run(1)
+        with pytest.raises(pk.PinnError, match="did not deliver"):
+            tr0.read()
+        first = time.time() - t0
+        assert 0.1 < first < 5.0                     # waited about the time-out (the sampler's set-size exchange, then the sums)
+        t0 = time.time()
+        tr0.run(3)                                   # poisoned: no further waiting
+        with pytest.raises(pk.PinnError, match="did not deliver"):
+            tr0.read()
+        assert time.time() - t0 < 0.2
+        with pytest.raises(pk.PinnError):
+            h0.dp_status()
+        theta_now = np.empty(1521)
+        h0.L.pinn_trainer_read(tr0.t, theta_now.ctypes.data_as(ctypes.c_void_p), None, None, None, None, None, 0)
+        assert np.array_equal(theta_now, th64)       # no optimizer step was applied with incomplete sums
+        tr0.close()
+    finally:
+        h0.dp_shutdown(); h1.dp_shutdown()
+        h0.close(); h1.close()
+
+
 @pytest.mark.skipif(not two_gpus(), reason="needs two GPUs")
 @pytest.mark.parametrize("n", [4096, 100003])
 def test_two_ranks_in_one_process_equal_the_whole_batch(golden_dir, n):

@@ -439,6 +439,18 @@ def test_calls_on_different_streams_of_one_handle_do_not_share_scratch(init_thet
             assert torch.equal(s[:7], s0[:7]) and torch.equal(g, g0)
 
 
+def test_roofline_measurement_helpers(init_theta):
+    """bench.py's denominators are measured by the library in the run: the FFMA rate of the device and the SM clock the
+    step kernel and the FFMA loop actually ran at (block 0 times itself)."""
+    h = pk.Handle.get(0)
+    flops, ms, mhz = h.measure_fp32_peak()
+    assert 55e12 < flops < 76e12 and 0.4 < ms < 0.8 and 1500 < mhz < 2100      # 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4e12
+    a32, m1, m2 = sample(0, 1 << 16, 5)
+    d = dev()
+    pk.loss_and_grad_raw(0, *[torch.from_numpy(a).to(d) for a in a32], torch.from_numpy(init_theta.astype(np.float32)).to(d))
+    assert 1200 < h.step_kernel_clock(torch.cuda.current_stream().cuda_stream) < 2100
+
+
 def test_empty_boundary_set_gives_nan_like_the_reference(init_theta):
     """mean over an empty selection is NaN in the reference (poc/main.py:349-350); same here."""
     tp = [torch.tensor(a, requires_grad=True) for a in layout.to_trainpy(init_theta)]

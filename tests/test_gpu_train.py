@@ -278,6 +278,52 @@ def test_train_drivers_reduce_the_loss(init_theta):
     assert set(loss) == {"Ltot", "Lpde", "Lbc", "Energy"}
 
 
+def test_paper_schedule_on_the_device_matches_the_reference_rerun(golden_dir):
+    """north star: 'reference-matching E(R) curves'.  The paper schedule (poc/main.py:919-942: 100 000 points x 5000 Adam steps
+    @ 8e-3, then 2000 fine-tune steps @ 5e-4 on the E-net from the saved best model) runs on the device in half a second and
+    is compared with the REAL reference run of the same schedule (tests/golden/poc_paper_run_seed0.npz, made on the CPU by
+    tests/golden/make_paper_run.py: 85 minutes) and with exactE() (poc/main.py:48-61).
+
+    What the reference itself delivers when re-run (seed 0): max|E_net - exact| = 1.8e-2 after the main stage, 2.4e-2 (R >= 1)
+    / 1.9e-2 (R >= 2) after the fine-tune, min Ltot 4.5e-7 / 4.2e-7 - the authors' own table (poc/energy_R_ion.pkl, 6.4e-3 /
+    3.1e-3) is a better draw of the same procedure: their checkpoint BEFORE the fine-tune has 2.1e-2 as well, and 2000 steps
+    move E_net only part of the way to where it is heading (below).  The runs use different random streams (torch CPU vs
+    Philox), so the comparison is statistical: bars = 1.5 x the reference rerun's own errors.  Measured on B200
+    (profiles/r02_*_acceptance.txt), seeds 0 / 1 / 2: 2.0e-2 / 5.0e-2 / 1.7e-2 (R >= 1), 1.9e-2 / 1.9e-2 / 1.6e-2 (R >= 2)."""
+    ref = np.load(os.path.join(golden_dir, "poc_paper_run_seed0.npz"))
+    Rt, Eex = ref["R"], ref["E_exact"]
+    err = lambda th, lo: float(np.abs(_enet_np(th, Rt) - Eex)[Rt >= lo - 1e-9].max())
+    theta0 = pk.init_poc(0)
+    assert np.array_equal(theta0, ref["theta_init"])                     # same starting point as the reference run
+    ref_err = {k: (err(ref["theta_" + k + "_saved"], 1.0), err(ref["theta_" + k + "_saved"], 2.0)) for k in ("stage1", "stage2")}
+    assert abs(ref_err["stage2"][0] - 2.356e-2) < 1e-4 and abs(ref_err["stage2"][1] - 1.894e-2) < 1e-4
+    last1, saved1, loss1 = pk.train_poc(theta0, {"n_train": 100000, "epochs": 5000, "lr": 8e-3}, seed=0)
+    assert saved1 is not None and np.all(np.isfinite(loss1["Ltot"]))
+    assert loss1["Ltot"].min() < 2 * ref["loss1_Ltot"].min()             # 4.2e-7 measured vs 4.46e-7
+    assert err(saved1, 1.0) < 1.5 * max(ref_err["stage1"][0], ref_err["stage2"][0])
+    last2, saved2, loss2 = pk.train_poc(saved1, {"n_train": 100000, "epochs": 2000, "lr": 5e-4}, freezeUnits=True, seed=1000)
+    assert saved2 is not None and loss2["Ltot"].min() < 2 * ref["loss2_Ltot"].min()
+    frozen = np.ones(1521, bool)
+    frozen[OFFS[6]:OFFS[12]] = False
+    assert np.array_equal(saved2[frozen], saved1[frozen])                 # freezeBase + freezeDecayUnit (poc/main.py:305-319)
+    e1, e2 = err(saved2, 1.0), err(saved2, 2.0)
+    print("paper schedule on the device: max|E_net - exact| %.2e (R>=1) %.2e (R>=2); reference rerun %.2e / %.2e; authors' table 6.4e-03 / 3.1e-03"
+          % (e1, e2, ref_err["stage2"][0], ref_err["stage2"][1]))
+    assert e1 < 1.5 * ref_err["stage2"][0] and e2 < 1.5 * ref_err["stage2"][1]
+    # the two fine-tuned curves agree with each other as well as either agrees with the exact one
+    d = np.abs(_enet_np(saved2, Rt) - ref["E_net_stage2"])
+    assert d[Rt >= 2.0 - 1e-9].max() < 1.5e-2 and d[Rt >= 1.0 - 1e-9].max() < 3.5e-2
+    # where the fine-tune is heading: with psi frozen, the E(R) minimising mean(res^2) is the Rayleigh quotient of that psi
+    _, saved3, _ = pk.train_poc(saved1, {"n_train": 100000, "epochs": 40000, "lr": 5e-4}, freezeUnits=True, seed=2000)
+    for Rv in (1.0, 2.0, 3.0):
+        g = pk.analysis.grid_sums(saved3, Rv, n=400)
+        E_int = g["psiHpsi"] / g["psi2"]
+        E_net = float(_enet_np(saved3, np.array([Rv]))[0])
+        assert abs(E_net - E_int) < 3e-3, (Rv, E_net, E_int)             # measured 5e-5 / 1.5e-4 / 1.8e-3
+        exact = float(Eex[np.argmin(np.abs(Rt - Rv))])
+        assert exact - 1e-3 < E_int < exact + 2e-2                        # variational: above the exact energy, by ~1e-2
+
+
 # ---------------------------------------------------------------------------------------------
 # dense-grid quadrature and the E(R) curve
 # ---------------------------------------------------------------------------------------------

@@ -150,7 +150,15 @@ def part_c(seeds):
                 "E_net_after_2000": enet(final, np.array(Rs)).tolist(), "E_exact": [float(Eex[np.argmin(np.abs(Rt - Rv))]) for Rv in Rs],
                 "Ltot_tail_mean_last_100": float(loss3["Ltot"][-100:, 0].mean())}
         runs.append(row)
-    ref = {"authors_table_max_abs_err_vs_exact_R_ge_1": float(np.abs(Eref - Eex)[Rt >= 1.0 - 1e-9].max()),
+    rr = np.load(os.path.join(GOLD, "poc_paper_run_seed0.npz"))   # the real reference, re-run on the CPU (make_paper_run.py)
+    rerun = {}
+    for tag in ("stage1", "stage2"):
+        e = np.abs(rr["E_net_" + tag] - Eex)
+        L = rr["loss1_Ltot" if tag == "stage1" else "loss2_Ltot"]
+        rerun[tag] = {"max_abs_err_vs_exact_R_ge_1": float(e[Rt >= 1.0 - 1e-9].max()), "max_abs_err_vs_exact_R_ge_2": float(e[Rt >= 2.0 - 1e-9].max()),
+                      "Ltot_min": float(L.min()), "Ltot_tail_mean_last_100": float(L[-100:].mean()), "E_net": rr["E_net_" + tag].tolist()}
+    rerun["seconds_on_cpu"] = rr["seconds"].tolist()
+    ref = {"reference_rerun_seed0": rerun, "authors_table_max_abs_err_vs_exact_R_ge_1": float(np.abs(Eref - Eex)[Rt >= 1.0 - 1e-9].max()),
            "authors_table_max_abs_err_vs_exact_R_ge_2": float(np.abs(Eref - Eex)[Rt >= 2.0 - 1e-9].max()),
            "authors_loss_tail_main": 7.42e-07, "authors_loss_tail_fine_tune": 4.69e-07, "R": Rt.tolist(),
            "E_exact": Eex.tolist(), "E_net_authors": Eref.tolist()}
@@ -198,6 +206,11 @@ def main():
         lines.append("   authors' table: max|E_net - exact| %.2e (R>=1) %.2e (R>=2); loss tails %.2e / %.2e"
                      % (r["authors_table_max_abs_err_vs_exact_R_ge_1"], r["authors_table_max_abs_err_vs_exact_R_ge_2"],
                         r["authors_loss_tail_main"], r["authors_loss_tail_fine_tune"]))
+        for tag, nm in (("stage1", "main"), ("stage2", "fine_tune")):
+            t = r["reference_rerun_seed0"][tag]
+            lines.append("   REAL reference re-run on the CPU, seed 0, %-9s: max|E_net - exact| %.2e (R>=1) %.2e (R>=2); Ltot min %.2e, tail(100) %.2e; %.0f s"
+                         % (nm, t["max_abs_err_vs_exact_R_ge_1"], t["max_abs_err_vs_exact_R_ge_2"], t["Ltot_min"], t["Ltot_tail_mean_last_100"],
+                            r["reference_rerun_seed0"]["seconds_on_cpu"][0 if tag == "stage1" else 1]))
         for run in c["runs"]:
             for tag in ("main", "fine_tune"):
                 t = run[tag]
@@ -215,9 +228,9 @@ def main():
                     lines.append("      %.1f  %.4f  %.5f     %.5f      %.5f" % (Rv, lf["E_exact"][i], lf["E_net_after_2000"][i],
                                                                                lf["E_net"][i], lf["E_int_400cube"][i]))
         run = c["runs"][0]
-        lines.append("   R      exact     authors   this(seed %d)" % run["seed"])
-        for Rv, ex, au, me in zip(r["R"], r["E_exact"], r["E_net_authors"], run["fine_tune"]["E_net"]):
-            lines.append("   %.1f  %.4f  %.5f  %.5f" % (Rv, ex, au, me))
+        lines.append("   R      exact     authors   ref. re-run  this(seed %d)" % run["seed"])
+        for Rv, ex, au, rrun, me in zip(r["R"], r["E_exact"], r["E_net_authors"], r["reference_rerun_seed0"]["stage2"]["E_net"], run["fine_tune"]["E_net"]):
+            lines.append("   %.1f  %.4f  %.5f  %.5f     %.5f" % (Rv, ex, au, rrun, me))
     txt = "\n".join(lines)
     open(os.path.join(OUT, "acceptance.txt"), "w").write(txt + "\n")
     print(txt)
