@@ -704,8 +704,9 @@ def main():
             "roofline": {"bound": "fp32_ffma", "achieved": achieved / 1e12, "peak": fp32_peak / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "frac_of_nominal_74.4": achieved / FP32_PEAK_NOMINAL,
+                         "frac_of_round1_peak_72.0": achieved / FP32_PEAK_FALLBACK,
                          "peak_source": "FFMA rate measured in this run on this device (pinn_measure_fp32_peak: register-resident "
-                                        "FFMA loop, %.3f ms per timed kernel, clocks in `clocks`); MEASURED_PEAKS.json has no FP32 entry; "
+                                        "FFMA loop, best of 8 x 10 launches, %.3f ms per timed kernel, clocks in `clocks`); MEASURED_PEAKS.json has no FP32 entry; "
                                         "round-1 figure of the same loop: %.1f" % (fp32_ms, FP32_PEAK_FALLBACK / 1e12),
                          "flop_per_point": FLOP_PER_POINT,
                          # the SM clock each kernel actually ran at (block 0 times itself: clock64 / %globaltimer): the step

@@ -84,7 +84,7 @@ int pinn_set_engine(pinn_handle* h, int engine);
 int pinn_get_engine(pinn_handle* h);
 
 /* Measurement helper (bench.py's roofline denominator): the FP32 FFMA rate of this device right now, from a
- * register-resident loop of independent FFMA chains (best of 5 timings of ~0.3 ms each, CUDA events).
+ * register-resident loop of independent FFMA chains (best of 8 timings of 10 x ~0.55 ms each, CUDA events).
  * fma_per_s: fused multiply-adds per second (x2 = FLOP/s); ms: duration of one timed kernel; sm_mhz: the SM clock the
  * loop ran at (block 0 times itself with clock64 and %globaltimer).  Synchronous. */
 int pinn_measure_fp32_peak(pinn_handle* h, double* fma_per_s, double* ms, double* sm_mhz);

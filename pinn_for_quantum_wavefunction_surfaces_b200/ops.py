@@ -202,12 +202,25 @@ class _PinnLoss(torch.autograd.Function):
     def forward(ctx, variant, order, x, y, z, R, idx1, idx2, *params):
         if len(params) != 16:
             raise ValueError("expected the model's 16 parameter tensors")
-        xs, ys, zs, Rs = _col(x, "x"), _col(y, "y"), _col(z, "z"), _col(R, "R")
+        # (n,1) / (n,) contiguous columns are used where they lie: no slicing, no detach - only their pointers travel
+        if all(t.is_contiguous() and (t.dim() == 1 or (t.dim() == 2 and t.shape[1] == 1)) and t.dtype in _DT for t in (x, y, z, R)):
+            xs, ys, zs, Rs = x, y, z, R
+        else:
+            xs, ys, zs, Rs = _col(x, "x"), _col(y, "y"), _col(z, "z"), _col(R, "R")
         n = xs.numel()
         dev = xs.device
         pdt = params[0].dtype
-        grad_mask = P.grad_mask_from_requires_grad(params, order)
-        ctx.order, ctx.shapes, ctx.needs = order, [p.shape for p in params], [p.requires_grad for p in params]
+        # one pass over the parameters: which want a gradient, their shapes, and whether the kernel can read them in place
+        grad_mask, shapes, needs, direct = 0, [], [], dev.type == "cuda" and pdt in _DT
+        for k, p in enumerate(params):
+            need = p.requires_grad
+            if need:
+                grad_mask |= 1 << (k if order == "poc" else P.TRAINPY_TO_POC[k])
+            shapes.append(p.shape)
+            needs.append(need)
+            if direct and not (p.dtype == pdt and p.is_cuda and p.is_contiguous()):
+                direct = False
+        ctx.order, ctx.shapes, ctx.needs = order, shapes, needs
         r1, r2 = _rows(idx1), _rows(idx2)
         c1, c2 = r1.numel(), r2.numel()
         # the reference takes the mean of an empty selection -> NaN loss (hard part 6): weight inf
@@ -218,7 +231,6 @@ class _PinnLoss(torch.autograd.Function):
             mask = _mask_cache.get(h, n, r1, r2, dev, stream)
             if ys.dtype != xs.dtype or zs.dtype != xs.dtype or Rs.dtype != xs.dtype:
                 raise ValueError("x, y, z, R must share one dtype")
-            direct = pdt in _DT and all(p.dtype == pdt and p.is_cuda and p.is_contiguous() for p in params)
             out = torch.empty(8 + P.N_THETA, dtype=torch.float64, device=dev)
             E = torch.empty(n, dtype=pdt if pdt in _DT else torch.float32, device=dev)
             w = (ctypes.c_double * 3)(*weights)
