@@ -227,6 +227,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       ST4(&Hrow[(3 * NH + k4) ^ sx], h3[0], h3[1], h3[2], h3[3]);
     }
   }
+  TL(4);
   tc_wait_mma(c);
   TL(3);
 

@@ -35,16 +35,17 @@ buf = (ctypes.c_longlong * (16 * 32))()
 rc = h.L.pinn_debug_timeline(buf)
 assert rc == 0, rc
 tl = np.array(buf[:]).reshape(16, 32)
-names = {0: "tile start", 1: "fwd L1 + st done", 2: "fwd role barrier", 3: "fwd MMA done", 5: "fwd L2 done", 6: "group barrier",
+names = {0: "tile start", 1: "fwd L1 + st done", 2: "fwd role barrier", 4: "H stash written", 3: "fwd MMA done", 5: "fwd L2 done", 6: "group barrier",
          7: "bwd L2 + st done", 8: "bwd role barrier", 9: "dW mma.sync done", 10: "colsums done", 11: "bwd MMA done",
          12: "bwd L1 done", 15: "tile end"}
 nw = 12 if variant == 0 else 8
 t0 = tl[:nw, 0].min()
-print("warp role grp | " + " | ".join("%s" % names[k] for k in sorted(names)))
+order = [0, 1, 2, 4, 3, 5, 6, 7, 8, 9, 10, 11, 12, 15]
+print("warp role grp | " + " | ".join("%s" % names[k] for k in order))
 for wv in range(nw):
     role, grp = wv >> 2, wv & 3
     row = tl[wv]
-    print("%4d %4d %3d | " % (wv, role, grp) + " ".join("%6d" % (row[k] - t0 if row[k] else -1) for k in sorted(names)))
+    print("%4d %4d %3d | " % (wv, role, grp) + " ".join("%6d" % (row[k] - t0 if row[k] else -1) for k in order))
 print("tile length (warp 0): %d cycles" % (tl[0, 15] - tl[0, 0]))
 
 kb = (ctypes.c_longlong * 48)()
