@@ -264,6 +264,33 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
         // and this order is the measured one)
         accN = fmaf(woa[i], t.x, accN); accN = fmaf(woa[i + 1], t.y, accN);
         accD = fmaf(woa[i], gD.x, accD); accD = fmaf(woa[i + 1], gD.y, accD);
+#ifdef PINN_TMEM_PARK
+        if (STASH) {
+          // Everything the reverse sweep needs from this unit that does not depend on its seeds (lamN, lamD arrive after
+          // the mid-tile exchange), pre-multiplied with wo: the sweep is then 7 packed operations per pair instead of 29,
+          // and the six values go back IN PLACE into the tensor-memory columns V0,V1,V2,P00,P01,P11 were just read from
+          // (dead until the reverse MMA) - no shared-memory round trip.
+          const float2 wo2 = make_float2(woa[i], woa[i + 1]);
+          const float2 tppp = f2mul(tp, f2fma(f2bc(-6.0f), tp, f2bc(1.0f)));
+          const float2 Aq = f2mul(wo2, tp), Bq = f2mul(wo2, tpp);
+          const float2 B1 = f2mul(Bq, f2fma(f2bc(2.0f * al11), v1, f2mul(f2bc(al12), v2)));
+          const float2 B2 = f2mul(Bq, f2fma(f2bc(al12), v1, f2mul(f2bc(2.0f * al22), v2)));
+          const float2 Cq = f2mul(wo2, f2fma(tpp, v3, f2mul(tppp, Q)));
+          V0[j] = t.x; V0[j + 1] = t.y; V1[j] = Aq.x; V1[j + 1] = Aq.y; V2[j] = B1.x; V2[j + 1] = B1.y;
+          P00[j] = B2.x; P00[j + 1] = B2.y; P01[j] = Cq.x; P01[j + 1] = Cq.y; P11[j] = gD.x; P11[j + 1] = gD.y;
+        }
+      }
+    }
+    if (STASH) {
+      tc_st8f(t0 + F_V0 + j8, V0);
+      tc_st8f(t0 + F_V12 + j8, V1);
+      tc_st8f(t0 + F_V12 + NH + j8, V2);
+      tc_st8f(t0 + F_P + j8, P00);
+      tc_st8f(t0 + F_P + NH + j8, P01);
+      tc_st8f(t0 + F_P + 2 * NH + j8, P11);
+    }
+  }
+#else
         tt[i] = t.x; tt[i + 1] = t.y; va[i] = v1.x; va[i + 1] = v1.y; vb[i] = v2.x; vb[i + 1] = v2.y; vD[i] = v3.x; vD[i + 1] = v3.y;
       }
       if (STASH) {
@@ -274,6 +301,7 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       }
     }
   }
+#endif
   Nv = accN;
   Dv = accD;
 }
@@ -303,6 +331,46 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   float* Hrow = Hs + lane * ROWH;
   float* Grow = Gs + lane * ROWH;
   float dwo[NH];
+#ifdef PINN_TMEM_PARK
+  {
+    // the forward left {t, wo tp, wo tpp (2 al11 v1 + al12 v2), wo tpp (al12 v1 + 2 al22 v2), wo (tpp v3 + tppp Q), gD} of every
+    // hidden unit in the tensor-memory columns of V0,V1,V2,P00,P01,P11; with the seeds known the adjoints are
+    //   vbar0 = lamN A + lamD C, vbar1 = lamD B1, vbar2 = lamD B2, vbar3 = lamD A, dwo = lamN t + lamD gD.
+    // Eight units at a time: all six loads of a block precede its stores (vbar lo of channels 2, 3 lands on the block's
+    // own t / A columns), and a block's vbar goes to tensor memory and to the stash at once - nothing stays in registers.
+    const uint32_t t0 = c.tlane + cb;
+#pragma unroll
+    for (int j8 = 0; j8 < NH; j8 += 8) {
+      float T[8], A[8], B1[8], B2[8], C[8], GD[8];
+      tc_ld8(t0 + F_V0 + j8, T);
+      tc_ld8(t0 + F_V12 + j8, A);
+      tc_ld8(t0 + F_V12 + NH + j8, B1);
+      tc_ld8(t0 + F_P + j8, B2);
+      tc_ld8(t0 + F_P + NH + j8, C);
+      tc_ld8(t0 + F_P + 2 * NH + j8, GD);
+      tc_wait_ld(T); tc_wait_ld(A); tc_wait_ld(B1); tc_wait_ld(B2); tc_wait_ld(C); tc_wait_ld(GD);
+      float vb[4][8];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float2 a2 = make_float2(A[i], A[i + 1]);
+        const float2 v0 = f2fma(f2bc(lamN), a2, f2mul(f2bc(lamD), make_float2(C[i], C[i + 1])));
+        const float2 v1 = f2mul(f2bc(lamD), make_float2(B1[i], B1[i + 1]));
+        const float2 v2 = f2mul(f2bc(lamD), make_float2(B2[i], B2[i + 1]));
+        const float2 v3 = f2mul(f2bc(lamD), a2);
+        const float2 dw = f2fma(f2bc(lamN), make_float2(T[i], T[i + 1]), f2mul(f2bc(lamD), make_float2(GD[i], GD[i + 1])));
+        vb[0][i] = v0.x; vb[0][i + 1] = v0.y; vb[1][i] = v1.x; vb[1][i + 1] = v1.y;
+        vb[2][i] = v2.x; vb[2][i + 1] = v2.y; vb[3][i] = v3.x; vb[3][i + 1] = v3.y;
+        dwo[j8 + i] = dw.x; dwo[j8 + i + 1] = dw.y;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ch++) {
+        ST4(&Grow[(ch * NH + j8) ^ sx], vb[ch][0], vb[ch][1], vb[ch][2], vb[ch][3]);
+        ST4(&Grow[(ch * NH + j8 + 4) ^ sx], vb[ch][4], vb[ch][5], vb[ch][6], vb[ch][7]);
+        tc_st_split8(t0 + B_VB_HI + ch * NH + j8, t0 + B_VB_LO + ch * NH + j8, vb[ch]);
+      }
+    }
+  }
+#else
   {
     float vbar[4][NH];
 #pragma unroll
@@ -345,6 +413,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
 #pragma unroll
     for (int ch = 0; ch < 4; ch++) tc_st_split16<false>(t0 + B_VB_HI + ch * NH, t0 + B_VB_LO + ch * NH, vbar[ch]);
   }
+#endif
   TL(7);
   tc_role_sync(c);  // (also orders the stash writes above before the fragment loads below: bar.sync)
   TL(8);

@@ -91,6 +91,24 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
+__device__ __forceinline__ void tc_st8f(uint32_t taddr, const float (&x)[8]) {
+  uint32_t v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __float_as_uint(x[i]);
+  tc_st8(taddr, v);
+}
+// truncating split of 8 values, stored as hi / lo halves (reverse sweep)
+__device__ __forceinline__ void tc_st_split8(uint32_t t_hi, uint32_t t_lo, const float (&x)[8]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) split_tf32(x[i], hi[i], lo[i]);
+  tc_st8(t_hi, hi);
+  tc_st8(t_lo, lo);
+}
 // split 16 values and store them as the hi / lo halves of an A operand row.  RN: the round-to-nearest split of the
 // activations (three instructions, split_tf32_rn3: measured as accurate as the four-instruction form, -1.5 % time; forward
 // sweep: psi ~ 2e-5 at the boundary is a cancellation of O(0.1) terms, a common rounding direction of all points would
