@@ -265,6 +265,10 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
         accN = fmaf(woa[i], t.x, accN); accN = fmaf(woa[i + 1], t.y, accN);
         accD = fmaf(woa[i], gD.x, accD); accD = fmaf(woa[i + 1], gD.y, accD);
 #ifdef PINN_TMEM_PARK
+        // (Round-2 experiment, compiled out: -DPINN_TMEM_PARK.  Correct - same gradient to 1e-8 - and it takes 19 % of the
+        // shared-memory wavefronts and 1 k cycles out of the reverse layer-2 phase, but the tile only gets 3 % shorter in the
+        // instrumented build and 0.5 % in the product build (0.11388 vs 0.11449 ms, profiles/r02_p_*): the weight-gradient
+        // phase behind it grows by what the phase in front of it shrinks.  DESIGN.md section 9.)
         if (STASH) {
           // Everything the reverse sweep needs from this unit that does not depend on its seeds (lamN, lamD arrive after
           // the mid-tile exchange), pre-multiplied with wo: the sweep is then 7 packed operations per pair instead of 29,
