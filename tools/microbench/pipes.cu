@@ -179,6 +179,34 @@ __global__ void k_mma_tf32(float* out, const float* in) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// legacy mma.sync m16n8k16 bf16 / f16 (fp32 accumulate), 8 independent accumulators: is the half-precision legacy path
+// faster per MAC than the TF32 one?  (It decides whether the cross terms of a 3xTF32 weight-gradient contraction are worth
+// moving to bf16.)
+template <int KIND>  // 0: bf16, 1: f16
+__global__ void k_mma_h16(float* out, const float* in) {
+  float c[8][4];
+  unsigned a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = 0x3c003c00u + threadIdx.x + i;
+  b[0] = 0x3c003c00u; b[1] = 0x3c003c01u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) c[i][j] = in[i + j];
+  for (int it = 0; it < ITERS / 4; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (KIND == 0)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  }
+  float s = 0; for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) s += c[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <typename F>
 static void run(const char* name, F launch, double ops_per_thread, int threads, int blocks, const char* unit) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -213,6 +241,11 @@ int main() {
   run("mix_16ffma_2mufu", [&] { k_mix<<<B, T>>>(out, in); }, ITERS * 16.0, T, B, "FMA/s");
   run("shfl_xor", [&] { k_shfl<<<B, T>>>(out, in); }, ITERS / 4 * 8.0, T, B, "SHFL-lane/s");
   run("mma_sync_tf32_m16n8k8", [&] { k_mma_tf32<<<B, T>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, T, B, "MAC/s");
+  run("mma_sync_bf16_m16n8k16", [&] { k_mma_h16<0><<<B, T>>>(out, in); }, ITERS / 4 * 8.0 * 2048.0 / 32.0, T, B, "MAC/s");
+  run("mma_sync_f16_m16n8k16", [&] { k_mma_h16<1><<<B, T>>>(out, in); }, ITERS / 4 * 8.0 * 2048.0 / 32.0, T, B, "MAC/s");
+  // 4 warps per SM (one per sub-core): what a single warp's 8 independent chains get
+  run("mma_sync_tf32_m16n8k8_1warp_per_subcore", [&] { k_mma_tf32<<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
+  run("mma_sync_bf16_m16n8k16_1warp_per_subcore", [&] { k_mma_h16<0><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 2048.0 / 32.0, 128, 148, "MAC/s");
   // long FP32 run to read the sustained clock with nvidia-smi
   for (int i = 0; i < 400; i++) k_ffma2<16><<<B, T>>>(out, in);
   CK(cudaDeviceSynchronize());
