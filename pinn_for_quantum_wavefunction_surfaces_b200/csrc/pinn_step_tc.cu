@@ -56,10 +56,13 @@ namespace pinn {
 
 template <int NEV>
 __host__ __device__ constexpr int tc_group_stash_floats() { return NEV * EVAL_STASH + ENET_STASH; }
+// geometry hand-off: the E-net warp of a group computes the per-point geometry once and publishes it to the group's MLP
+// warps: 12 floats per point {f1, f2, ir1, ir2 | al1, al2, al11, al12 | al22, dx1, dx2, set bits}, two buffers
+constexpr int GEO_BYTES = 2 * 128 * 12 * 4;
 template <int NEV>
 __host__ __device__ constexpr size_t tc_smem_bytes() {
   return WTS_TC_BYTES + 64 /*mbarriers + tmem base*/ + sizeof(float2) * 4 * 2 * 3 * 32 + sizeof(float) * 4 * tc_group_stash_floats<NEV>() +
-         COORD_STAGES * COORD_STAGE_BYTES;
+         COORD_STAGES * COORD_STAGE_BYTES + GEO_BYTES;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -183,6 +186,9 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
   TL(1);
   tc_role_sync(c);
   TL(2);
+  // (One issuing warp per role.  Letting three warps issue six MMAs each - one accumulator region per warp, four commits on
+  // the role's mbarrier - gives the same bits and a 0.9 % SLOWER step (0.11294 vs 0.11196 ms, profiles/r02_t_ab_issue.log),
+  // although the single issuer runs ~350 cycles behind its peers in the timeline.)
   if (c.issuer && elect_one()) {
     tc_fence_after();
     const uint32_t d = c.tbase + cb;
@@ -777,7 +783,8 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   uint64_t* cfull = reinterpret_cast<uint64_t*>(smem_raw + WTS_TC_BYTES + 40);  // [COORD_STAGES]: bulk coordinate copies landed
   float2* mbox = reinterpret_cast<float2*>(smem_raw + WTS_TC_BYTES + 64);
   float* stash = reinterpret_cast<float*>(smem_raw + WTS_TC_BYTES + 64 + sizeof(float2) * G * 2 * 3 * 32);
-  unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - COORD_STAGES * COORD_STAGE_BYTES;
+  unsigned char* cstage = smem_raw + tc_smem_bytes<NEV>() - COORD_STAGES * COORD_STAGE_BYTES - GEO_BYTES;
+  float4* geo = reinterpret_cast<float4*>(smem_raw + tc_smem_bytes<NEV>() - GEO_BYTES);  // [2][128][3]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role/group branches and MMA operands
@@ -944,9 +951,37 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       if (it < 38) TLK(2 + it);
       const unsigned char* cbuf = cstage + (it % COORD_STAGES) * COORD_STAGE_BYTES;
       const bool this_bulk = tile_bulk(st);   // (its arrival was awaited by the E-net warps before the last group barrier)
-      const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
-      const Geom g = geom_from_raw(raw);
-      const float cur_dx1 = raw.dx1, cur_dx2 = raw.dx2;
+      // The E-net warp (it runs ~2 k cycles ahead of the MLP warps of its group and waits for them mid-tile anyway) forms the
+      // geometry of the group's 32 points once and hands it over: the MLP warps - the critical path - start their tile with
+      // three 128-bit loads instead of the rsqrt / exp chain (same bits, step -1.5 %: 0.11255 vs 0.11427 ms on one box,
+      // profiles/r02_q_ab_geometry_handoff.log).  arrive (E-net) + sync (MLP) on a named barrier per group; two buffers, and
+      // the E-net warp cannot be two tiles ahead (mid-tile group barrier).
+      Geom g;
+      float cur_dx1, cur_dx2, mk_f = 0.0f;
+      {
+        float4* gp = geo + ((it & 1) * 128 + slot) * 3;
+        if (!IS_MLP) {
+          const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
+          g = geom_from_raw(raw);
+          cur_dx1 = raw.dx1; cur_dx2 = raw.dx2;
+          if (TRAIN && p.mask) {  // bulk stage: the 128 mask bytes as they lie; per-lane stage: the aligned word around the byte
+            const unsigned mk = this_bulk ? (unsigned)cbuf[4 * COORD_COL_BYTES + slot]
+                                          : *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
+            mk_f = (float)(mk & 3u);
+          }
+          gp[0] = make_float4(g.f1, g.f2, g.ir1, g.ir2);
+          gp[1] = make_float4(g.al1, g.al2, g.al11, g.al12);
+          gp[2] = make_float4(g.al22, cur_dx1, cur_dx2, mk_f);
+          asm volatile("bar.arrive %0, %1;" ::"r"(8 + grp), "r"((NEV + 1) * 32) : "memory");
+        } else {
+          named_barrier(8 + grp, (NEV + 1) * 32);
+          const float4 q0 = gp[0], q1 = gp[1], q2 = gp[2];
+          g.f1 = q0.x; g.f2 = q0.y; g.ir1 = q0.z; g.ir2 = q0.w;
+          g.al1 = q1.x; g.al2 = q1.y; g.al11 = q1.z; g.al12 = q1.w;
+          g.al22 = q2.x; cur_dx1 = q2.y; cur_dx2 = q2.z; mk_f = q2.w;
+          g.R = 0.0f;  // only the E-net warp uses R
+        }
+      }
       if (stager) {  // coordinates COORD_AHEAD super-tiles ahead: in flight while this one (and the next) is computed
         const long long in = pidx + (long long)COORD_AHEAD * gridDim.x * 128;
         const long long stn = st + (long long)COORD_AHEAD * gridDim.x;
@@ -1046,8 +1081,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       // ---- seeds of the reverse sweep (oracle/closed_form.py:loss_and_grad) ----
       float m1f, m2f;
       if (p.mask) {
-        const unsigned mk = this_bulk ? (unsigned)cbuf[4 * COORD_COL_BYTES + slot]   // bulk: the 128 mask bytes as they lie
-                                      : *(const uint32_t*)(cbuf + 4 * COORD_COL_BYTES + slot * 4) >> (8u * (unsigned)((uintptr_t)(p.mask + pi) & 3u));
+        const unsigned mk = (unsigned)mk_f;   // the two set bits came with the geometry
         m1f = (mk & 1u) ? 1.0f : 0.0f;
         m2f = (mk & 2u) ? 1.0f : 0.0f;
       } else {
