@@ -478,6 +478,9 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   for (int j4 = 0; j4 < NH; j4 += 4) ST4(&Grow[(NH + j4) ^ sx], dwo[j4], dwo[j4 + 1], dwo[j4 + 2], dwo[j4 + 3]);
   __syncwarp();
   TL(9);
+  // (Handing these column sums to the group's E-net warp - it has finished its own tile by then - keeps the bits and makes the
+  // step 0.9 % SLOWER, 0.11338 vs 0.11233 ms, profiles/r02_v_ab_colsum_handoff.log: after the geometry hand-off the E-net
+  // role has no slack left to give.)
   acc2(acc.s0, colsum2<ROWH>(Gs, 2 * (lane & 15), lane >> 4));
 
   // ---- hbar = W2^T vbar is in TMEM now: layer-1 reverse sweep ----
@@ -956,9 +959,15 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       // three 128-bit loads instead of the rsqrt / exp chain (same bits, step -1.5 %: 0.11255 vs 0.11427 ms on one box,
       // profiles/r02_q_ab_geometry_handoff.log).  arrive (E-net) + sync (MLP) on a named barrier per group; two buffers, and
       // the E-net warp cannot be two tiles ahead (mid-tile group barrier).
+      // Training launches only: without a reverse sweep the E-net role is not ahead of the MLP roles, and waiting for it
+      // cost the 10^8-point grid quadrature 8 % (7.6e9 vs 8.2e9 points/s) - there every role forms its own geometry.
       Geom g;
       float cur_dx1, cur_dx2, mk_f = 0.0f;
-      {
+      if (!TRAIN) {
+        const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
+        g = geom_from_raw(raw);
+        cur_dx1 = raw.dx1; cur_dx2 = raw.dx2;
+      } else {
         float4* gp = geo + ((it & 1) * 128 + slot) * 3;
         if (!IS_MLP) {
           const RawPt raw = p.grid.on ? tc_grid_point(p, pi) : coord_stage_read(p, cbuf, slot);
