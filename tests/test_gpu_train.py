@@ -146,6 +146,35 @@ def test_trainer_equals_step_by_step_host_loop(variant, init_theta):
     assert np.allclose(res[True]["history"][:, 3], col3, rtol=1e-12)
 
 
+def test_trainer_in_flight_does_not_disturb_calls_on_other_streams(init_theta):
+    """Trainer.run() is asynchronous on the trainer's own stream; evaluations on torch's stream (and a second
+    trainer) while it is in flight used to share the handle's partial-row workspace.  Every stream has its own now: the
+    results are those of the same calls made alone, and the trainers' trajectories those of trainers run alone."""
+    n, steps = 1 << 16, 120
+    alone = {}
+    for seed in (11, 22):
+        tr = pk.Trainer("poc", n, init_theta, seed=seed, lr=8e-3, history_capacity=steps)
+        tr.run(steps)
+        alone[seed] = tr.read()
+        tr.close()
+    b = pk.sample(50000, 5, 0)
+    th = torch.from_numpy(init_theta.astype(np.float32)).to(dev())
+    s0, g0, _ = pk.loss_and_grad_raw(0, b["x"], b["y"], b["z"], b["R"], th, b["mask"], b["weights"])
+    s0, g0 = s0.clone(), g0.clone()
+    torch.cuda.synchronize()
+    t1 = pk.Trainer("poc", n, init_theta, seed=11, lr=8e-3, history_capacity=steps)
+    t2 = pk.Trainer("poc", n, init_theta, seed=22, lr=8e-3, history_capacity=steps)
+    t1.run(steps)                       # both return at once; ~2 x 120 steps of work are now queued on two streams
+    t2.run(steps)
+    for _ in range(40):                 # ... and these run concurrently with them on torch's stream
+        s, g, _ = pk.loss_and_grad_raw(0, b["x"], b["y"], b["z"], b["R"], th, b["mask"], b["weights"])
+        assert torch.equal(s[:7], s0[:7]) and torch.equal(g, g0)
+    r1, r2 = t1.read(), t2.read()
+    t1.close(); t2.close()
+    for r, seed in ((r1, 11), (r2, 22)):
+        assert np.array_equal(r["theta"], alone[seed]["theta"]) and np.array_equal(r["history"], alone[seed]["history"])
+
+
 def test_trainer_freeze_and_resample_schedule(init_theta):
     """poc/main.py:396: resample iff tt % sc_sampling == 0 and tt < 0.9*epochs."""
     tr = pk.Trainer("poc", 2048, init_theta, sc_sampling=2, freeze_after=5, history_capacity=10)
