@@ -370,7 +370,7 @@ def seam_e2e(pk, dev, n, steps):
     def loop(device, bs, K):
         model = IonParams(load_theta()).to(device)
         opt = torch.optim.Adam(model.parameters(), lr=1e-7, weight_decay=0)
-        hist = np.zeros((K + 5, 4))
+        Ltot_h, Lpde_h, Lbc_h, E_h = (np.zeros([K + 5, 1]) for _ in range(4))   # the reference's history arrays (main.py:375-378)
         split = {"LossFunctions": 0.0, "backward": 0.0, "optimizer.step": 0.0, "history .cpu()": 0.0}
         pc = time.perf_counter
         for tt in range(K + 5):
@@ -388,15 +388,15 @@ def seam_e2e(pk, dev, n, steps):
             t2 = pc()
             opt.step()
             t3 = pc()
-            hist[tt, 0] = Ltot.cpu().data.numpy(); hist[tt, 1] = LossPDE.cpu().data.numpy()
-            hist[tt, 2] = Lbc.cpu().data.numpy(); hist[tt, 3] = E[-1].cpu().data.numpy()
+            Ltot_h[tt] = Ltot.cpu().data.numpy(); Lpde_h[tt] = LossPDE.cpu().data.numpy()     # main.py:408-411, literally
+            Lbc_h[tt] = Lbc.cpu().data.numpy(); E_h[tt] = E[-1].cpu().data.numpy()
             t4 = pc()
             split["LossFunctions"] += t1 - t0; split["backward"] += t2 - t1
             split["optimizer.step"] += t3 - t2; split["history .cpu()"] += t4 - t3
         if device.type == "cuda":
             torch.cuda.synchronize()
         dt = (pc() - t_start) / K
-        return {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": K, "loss": float(hist[-1, 0]),
+        return {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": K, "loss": float(Ltot_h[-1, 0]),
                 "host_ms_per_step": {k: round(v / K * 1e3, 4) for k, v in split.items()}}
     cpu = torch.device("cpu")
     n_small = n
