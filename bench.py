@@ -398,14 +398,56 @@ def seam_e2e(pk, dev, n, steps):
         dt = (pc() - t_start) / K
         return {"value": n / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": K, "loss": float(Ltot_h[-1, 0]),
                 "host_ms_per_step": {k: round(v / K * 1e3, 4) for k, v in split.items()}}
+    def autograd_floor(device, K=200):
+        """What PyTorch itself charges for ANY op with this signature: a torch.autograd.Function with the same 24 inputs and
+        4 outputs that does nothing (one empty() in forward, one multiply and 16 views in backward), in the same loop."""
+        model = IonParams(load_theta()).to(device)
+        ps = tuple(model.parameters())
+        sizes = [p.numel() for p in ps]
+
+        class NoOp(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, variant, order, x, y, z, R, i1, i2, *params):
+                out = torch.zeros(8 + 1521, dtype=torch.float64, device=x.device)
+                E = torch.empty(x.shape[0], dtype=torch.float64, device=x.device).view(-1, 1)
+                ctx.save_for_backward(out[8:])
+                ctx.shapes = [p.shape for p in params]
+                L, a, b2 = out[0], out[1], out[2]
+                ctx.mark_non_differentiable(a, b2, E)
+                return L, a, b2, E
+
+            @staticmethod
+            def backward(ctx, g, *_):
+                (d,) = ctx.saved_tensors
+                parts = (d * g).split(sizes)
+                return (None,) * 8 + tuple(q if len(sh) == 1 else q.view(sh) for q, sh in zip(parts, ctx.shapes))
+        x = torch.zeros(n, 1, dtype=torch.float64, device=device)
+        tf = tb = 0.0
+        pc = time.perf_counter
+        for tt in range(K + 5):
+            if tt == 5:
+                tf = tb = 0.0
+            for p in ps:
+                p.grad = None
+            t0 = pc()
+            L = NoOp.apply(0, "poc", x, x, x, x, None, None, *ps)[0]
+            t1 = pc()
+            L.backward()
+            t2 = pc()
+            tf += t1 - t0; tb += t2 - t1
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+        return {"forward_ms": round(tf / K * 1e3, 4), "backward_ms": round(tb / K * 1e3, 4)}
     cpu = torch.device("cpu")
     n_small = n
     res = {"cuda_resident": loop(dev, batches(dev, 8), steps),
            "cuda_resident_frozen_batch": loop(dev, batches(dev, 1), steps),
            "cpu_resident_pageable": loop(cpu, batches(cpu, 8), max(5, steps // 4)),
            "cpu_resident_pinned": loop(cpu, batches(cpu, 8, pin=True), max(5, steps // 4)),
+           "autograd_floor_cuda": autograd_floor(dev),
            "e2e_fraction_note": "per step the loop spends ~0.26 ms in torch.optim.Adam.step and ~0.1 ms in the four .cpu() reads on the "
-                                "host - the reference's own lines - against 0.14 ms for a whole e2e step; the seam is host-bound at "
+                                "host - the reference's own lines - against 0.14 ms for a whole e2e step; autograd_floor_cuda is what a "
+                                "torch.autograd.Function with the same 24 inputs costs when it does nothing; the seam is host-bound at "
                                 "2^18 points and GPU-bound from ~2^21 points per step on (cuda_resident_4M_points)",
            "what": "reference loop body (poc/main.py:394-411) on the patched LossFunctions: zero_grad, LossFunctions, backward, "
                    "torch.optim.Adam.step, 4 history reads with .cpu(); float64 (n,1) tensors + torch.where index tuples; "
