@@ -1,4 +1,4 @@
-// Launch parameters and host-side launchers shared by pinn_kernels.cu and pinn_capi.cu.
+// Launch parameters and host-side launchers shared by the kernel files (pinn_step_tc.cu, pinn_reduce.cu, pinn_train.cu) and pinn_capi.cu.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -81,7 +81,7 @@ cudaError_t launch_count(const StepParams& p, unsigned long long* counts, double
 // Data-parallel exchange fused into the reduction kernel: every rank owns one exchange buffer that all
 // peers of the box can write through NVLink peer memory (cudaIpc / peer access).
 //   rows [2 slots][DP_MAX_WORLD][NPART] x 16 B : rank r deposits its reduced row in slot (step & 1), index r, of EVERY
-//        rank; each float64 is two 8-byte words {32 data bits, 32-bit step number} (pinn_kernels.cu: reduce_partials_kernel)
+//        rank; each float64 is two 8-byte words {32 data bits, 32-bit step number} (pinn_reduce.cu: reduce_partials_kernel)
 //   ctl  8 x u64 {exchanges completed, blocks done, status, set-count exchanges completed, ...}
 //   cnt  [2 slots][DP_MAX_WORLD][2] x 8 B : the sampler's boundary-set sizes, same {data, step} words (pinn_train.cu)
 constexpr int DP_MAX_WORLD = 8;
