@@ -88,36 +88,61 @@ static void ws_free(pinn_workspace& w) {
   w = pinn_workspace();
 }
 
+// The owner of `st` is about to destroy it (a trainer): drain it and give the workspace back.
+void ws_release(pinn_handle* h, cudaStream_t st) {
+  for (pinn_workspace& c : h->ws)
+    if (c.stream == st && c.partials) {
+      cudaStreamSynchronize(st);
+      ws_free(c);
+    }
+}
+
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cap != cudaStreamCaptureStatusNone;
+}
+
 pinn_workspace* ws_for(pinn_handle* h, cudaStream_t st, int rows) {
   constexpr size_t MAX_WS = 32;
   pinn_workspace* w = nullptr;
   for (pinn_workspace& c : h->ws)
     if (c.stream == st && c.partials) { w = &c; break; }
   if (w && w->rows >= rows) {
+    // a CUDA graph captured from this stream carries the workspace's addresses: from then on it is never recycled
+    if (!w->in_graph && stream_is_capturing(st)) w->in_graph = true;
     w->last_use = ++h->ws_clock;
     return w;
   }
   // first call on this stream (or more rows than before): allocate.  Not possible while the stream is being captured
   // into a CUDA graph - the caller has to make one plain call first.
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-  if (cap != cudaStreamCaptureStatusNone) {
+  if (stream_is_capturing(st)) {
     fail(h, PINN_EINVAL, "first call on a stream under CUDA-graph capture: call once on this stream outside the capture first");
     return nullptr;
   }
   if (!w) {
-    if (h->ws.size() >= MAX_WS) {  // streams come and go in the caller: recycle the least recently used workspace
-      size_t lru = 0;
-      for (size_t i = 1; i < h->ws.size(); i++)
-        if (h->ws[i].last_use < h->ws[lru].last_use) lru = i;
+    for (pinn_workspace& c : h->ws)
+      if (!c.partials) { w = &c; break; }  // a released slot
+    if (!w && h->ws.size() >= MAX_WS) {  // streams come and go in the caller: recycle the least recently used workspace
+      size_t lru = h->ws.size();
+      for (size_t i = 0; i < h->ws.size(); i++)
+        if (!h->ws[i].in_graph && h->ws[i].stream != h->s_main && (lru == h->ws.size() || h->ws[i].last_use < h->ws[lru].last_use)) lru = i;
+      if (lru == h->ws.size()) {
+        fail(h, PINN_EINVAL, "more than 32 streams with captured graphs or trainers on one handle");
+        return nullptr;
+      }
       cudaDeviceSynchronize();      // its last kernels may still be running
       ws_free(h->ws[lru]);
       w = &h->ws[lru];
-    } else {
+    } else if (!w) {
       h->ws.emplace_back();
       w = &h->ws.back();
     }
   } else {
+    if (w->in_graph) {
+      fail(h, PINN_EINVAL, "this stream's workspace is referenced by a captured graph and cannot grow");
+      return nullptr;
+    }
     cudaStreamSynchronize(st);
     ws_free(*w);
   }

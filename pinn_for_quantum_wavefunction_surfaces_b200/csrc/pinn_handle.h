@@ -22,6 +22,7 @@ struct pinn_workspace {
   unsigned long long* counts = nullptr;  // [0..1] boundary-set sizes, [2] batch index of pinn_sample, [3] its block ticket
   double* grid_partials = nullptr;  // [sm_count + 1][8] dense-grid quadrature rows
   uint64_t last_use = 0;
+  bool in_graph = false;            // a call on this stream was captured into a CUDA graph: the addresses above must stay valid
 };
 
 struct pinn_handle {
@@ -112,6 +113,7 @@ int loss_fwd_bwd_impl(pinn_handle* h, const LossCall& c, cudaStream_t st);
 // The workspace of stream `st` with room for at least `rows` partial rows (created / grown on first use; the handle mutex
 // is held by the caller).  NULL + error message on failure.
 pinn_workspace* ws_for(pinn_handle* h, cudaStream_t st, int rows);
+void ws_release(pinn_handle* h, cudaStream_t st);
 
 extern std::string g_create_err;
 

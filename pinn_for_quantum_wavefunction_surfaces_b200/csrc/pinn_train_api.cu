@@ -284,7 +284,13 @@ int pinn_trainer_destroy(pinn_trainer* t) {
   cudaFree(t->E); cudaFree(t->theta32); cudaFree(t->batch); cudaFree(t->step); cudaFree(t->best_step); cudaFree(t->adam_ticket);
   cudaFree(t->theta); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad); cudaFree(t->sums);
   cudaFree(t->best_loss); cudaFree(t->best_theta); cudaFree(t->hist);
-  if (t->st) cudaStreamDestroy(t->st);
+  if (t->st) {
+    {
+      std::lock_guard<std::mutex> lk(t->h->mu);
+      ws_release(t->h, t->st);  // the stream handle dies here: its workspace (referenced by the graphs above) goes with it
+    }
+    cudaStreamDestroy(t->st);
+  }
   delete t;
   return 0;
 }

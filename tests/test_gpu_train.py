@@ -175,6 +175,39 @@ def test_trainer_in_flight_does_not_disturb_calls_on_other_streams(init_theta):
         assert np.array_equal(r["theta"], alone[seed]["theta"]) and np.array_equal(r["history"], alone[seed]["history"])
 
 
+def test_workspace_recycling_spares_streams_whose_calls_were_captured(init_theta):
+    """A handle keeps at most 32 per-stream workspaces and recycles the least recently used one.  A trainer's captured
+    graphs carry its workspace's addresses, so that one must survive any number of other streams coming and going; a
+    closed trainer gives its workspace back."""
+    n, steps = 4096, 8
+    ref = pk.Trainer("poc", n, init_theta, seed=3, lr=8e-3, history_capacity=2 * steps)
+    ref.run(2 * steps)
+    want = ref.read()
+    ref.close()
+    tr = pk.Trainer("poc", n, init_theta, seed=3, lr=8e-3, history_capacity=2 * steps)
+    tr.run(steps)                                         # graphs captured here
+    tr.read()
+    b = pk.sample(3000, 5, 0)
+    th = torch.from_numpy(init_theta.astype(np.float32)).to(dev())
+    s0, g0, _ = pk.loss_and_grad_raw(0, b["x"], b["y"], b["z"], b["R"], th, b["mask"], b["weights"])
+    s0, g0 = s0.clone(), g0.clone()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(40)]    # more streams than workspaces: the oldest are recycled
+    for st in streams:
+        with torch.cuda.stream(st):
+            s, g, _ = pk.loss_and_grad_raw(0, b["x"], b["y"], b["z"], b["R"], th, b["mask"], b["weights"])
+        st.synchronize()
+        assert torch.equal(s[:7], s0[:7]) and torch.equal(g, g0)
+    for _ in range(40):                                   # trainers come and go: their slots are given back
+        t = pk.Trainer("poc", 512, init_theta, seed=1, history_capacity=2)
+        t.run(2)
+        t.close()
+    tr.run(steps)                                         # graph replay after all that
+    got = tr.read()
+    tr.close()
+    assert np.array_equal(got["theta"], want["theta"]) and np.array_equal(got["history"], want["history"])
+
+
 def test_trainer_freeze_and_resample_schedule(init_theta):
     """poc/main.py:396: resample iff tt % sc_sampling == 0 and tt < 0.9*epochs."""
     tr = pk.Trainer("poc", 2048, init_theta, sc_sampling=2, freeze_after=5, history_capacity=10)
