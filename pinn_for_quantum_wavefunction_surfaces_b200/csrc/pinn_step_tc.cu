@@ -253,7 +253,6 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
     for (int j4 = 0; j4 < 8; j4 += 4) {
       const float4 b2v = LD4(&w.b2s[j8 + j4]), wov = LD4(&w.wo[j8 + j4]);
       const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, woa[4] = {wov.x, wov.y, wov.z, wov.w};
-      float tt[4], va[4], vb[4], vD[4];
 #pragma unroll
       for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction; the sigmoid (MUFU) stays scalar
         const int j = j4 + i;
@@ -270,16 +269,14 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
         // and this order is the measured one)
         accN = fmaf(woa[i], t.x, accN); accN = fmaf(woa[i + 1], t.y, accN);
         accD = fmaf(woa[i], gD.x, accD); accD = fmaf(woa[i + 1], gD.y, accD);
-#ifdef PINN_TMEM_PARK
-        // (Round-2 experiment, compiled out: -DPINN_TMEM_PARK.  Correct - same gradient to 1e-8 - and it takes 19 % of the
-        // shared-memory wavefronts and 1 k cycles out of the reverse layer-2 phase, but the tile only gets 3 % shorter in the
-        // instrumented build and 0.5 % in the product build (0.11388 vs 0.11449 ms, profiles/r02_p_*): the weight-gradient
-        // phase behind it grows by what the phase in front of it shrinks.  DESIGN.md section 9.)
         if (STASH) {
           // Everything the reverse sweep needs from this unit that does not depend on its seeds (lamN, lamD arrive after
           // the mid-tile exchange), pre-multiplied with wo: the sweep is then 7 packed operations per pair instead of 29,
           // and the six values go back IN PLACE into the tensor-memory columns V0,V1,V2,P00,P01,P11 were just read from
-          // (dead until the reverse MMA) - no shared-memory round trip.
+          // (dead until the reverse MMA) - no shared-memory round trip (19 % fewer shared-memory wavefronts).
+          // v14: on its own this shortened the MLP roles' tile and the step by 0.3-0.5 % only - the E-net role was within
+          // ~300 cycles of the critical path (profiles/r02_ae_*) - and the packed E-net arithmetic on its own made the step
+          // 2 % slower; together they take 2.9 % off the step (profiles/r02_ag_*, r02_ai_*).  DESIGN.md section 9.
           const float2 wo2 = make_float2(woa[i], woa[i + 1]);
           const float2 tppp = f2mul(tp, f2fma(f2bc(-6.0f), tp, f2bc(1.0f)));
           const float2 Aq = f2mul(wo2, tp), Bq = f2mul(wo2, tpp);
@@ -300,18 +297,6 @@ __device__ __forceinline__ void tc_mlp_forward(const Wts& w, TcCtx& c, uint32_t 
       tc_st8f(t0 + F_P + 2 * NH + j8, P11);
     }
   }
-#else
-        tt[i] = t.x; tt[i + 1] = t.y; va[i] = v1.x; va[i + 1] = v1.y; vb[i] = v2.x; vb[i + 1] = v2.y; vD[i] = v3.x; vD[i + 1] = v3.y;
-      }
-      if (STASH) {
-        ST4(&Grow[(0 * NH + j8 + j4) ^ sx], tt[0], tt[1], tt[2], tt[3]);
-        ST4(&Grow[(1 * NH + j8 + j4) ^ sx], va[0], va[1], va[2], va[3]);
-        ST4(&Grow[(2 * NH + j8 + j4) ^ sx], vb[0], vb[1], vb[2], vb[3]);
-        ST4(&Grow[(3 * NH + j8 + j4) ^ sx], vD[0], vD[1], vD[2], vD[3]);
-      }
-    }
-  }
-#endif
   Nv = accN;
   Dv = accD;
 }
@@ -341,7 +326,6 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
   float* Hrow = Hs + lane * ROWH;
   float* Grow = Gs + lane * ROWH;
   float dwo[NH];
-#ifdef PINN_TMEM_PARK
   {
     // the forward left {t, wo tp, wo tpp (2 al11 v1 + al12 v2), wo tpp (al12 v1 + 2 al22 v2), wo (tpp v3 + tppp Q), gD} of every
     // hidden unit in the tensor-memory columns of V0,V1,V2,P00,P01,P11; with the seeds known the adjoints are
@@ -380,50 +364,6 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
       }
     }
   }
-#else
-  {
-    float vbar[4][NH];
-#pragma unroll
-    for (int j4 = 0; j4 < NH; j4 += 4) {
-      const float4 tv = LD4(&Grow[(0 * NH + j4) ^ sx]), av = LD4(&Grow[(1 * NH + j4) ^ sx]);
-      const float4 bv = LD4(&Grow[(2 * NH + j4) ^ sx]), dv = LD4(&Grow[(3 * NH + j4) ^ sx]);
-      const float4 wov = LD4(&w.wo[j4]);
-      const float ta[4] = {tv.x, tv.y, tv.z, tv.w}, vaa[4] = {av.x, av.y, av.z, av.w};
-      const float vba[4] = {bv.x, bv.y, bv.z, bv.w}, vDa[4] = {dv.x, dv.y, dv.z, dv.w};
-      const float woa[4] = {wov.x, wov.y, wov.z, wov.w};
-#pragma unroll
-      for (int i = 0; i < 4; i += 2) {  // two hidden units per instruction (FFMA2 / FMUL2)
-        const int j = j4 + i;
-        const float2 t = make_float2(ta[i], ta[i + 1]), v1 = make_float2(vaa[i], vaa[i + 1]);
-        const float2 v2 = make_float2(vba[i], vba[i + 1]), v3 = make_float2(vDa[i], vDa[i + 1]);
-        const float2 wo2 = make_float2(woa[i], woa[i + 1]);
-        const float2 tp = f2fma(f2neg(t), t, t);
-        const float2 tpp = f2fma(f2mul(f2bc(-2.0f), t), tp, tp);
-        const float2 tppp = f2mul(tp, f2fma(f2bc(-6.0f), tp, f2bc(1.0f)));
-        const float2 Q = quad_form2(al11, al12, al22, v1, v2);
-        const float2 gD = f2fma(tp, v3, f2mul(tpp, Q));
-        const float2 tbar = f2mul(f2bc(lamN), wo2), gDbar = f2mul(f2bc(lamD), wo2);
-        const float2 dw = f2fma(f2bc(lamN), t, f2mul(f2bc(lamD), gD));
-        const float2 c2 = f2mul(gDbar, tpp);
-        const float2 vb3 = f2mul(gDbar, tp);
-        const float2 vb1 = f2mul(c2, f2fma(f2bc(2.0f * al11), v1, f2mul(f2bc(al12), v2)));
-        const float2 vb2 = f2mul(c2, f2fma(f2bc(al12), v1, f2mul(f2bc(2.0f * al22), v2)));
-        const float2 vb0 = f2fma(tbar, tp, f2mul(gDbar, f2fma(tpp, v3, f2mul(tppp, Q))));
-        dwo[j] = dw.x; dwo[j + 1] = dw.y;
-        vbar[3][j] = vb3.x; vbar[3][j + 1] = vb3.y;
-        vbar[1][j] = vb1.x; vbar[1][j + 1] = vb1.y;
-        vbar[2][j] = vb2.x; vbar[2][j + 1] = vb2.y;
-        vbar[0][j] = vb0.x; vbar[0][j + 1] = vb0.y;
-      }
-#pragma unroll
-      for (int ch = 0; ch < 4; ch++)
-        ST4(&Grow[(ch * NH + j4) ^ sx], vbar[ch][j4], vbar[ch][j4 + 1], vbar[ch][j4 + 2], vbar[ch][j4 + 3]);
-    }
-    const uint32_t t0 = c.tlane + cb;
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) tc_st_split16<false>(t0 + B_VB_HI + ch * NH, t0 + B_VB_LO + ch * NH, vbar[ch]);
-  }
-#endif
   TL(7);
   tc_role_sync(c);  // (also orders the stash writes above before the fragment loads below: bar.sync)
   TL(8);
@@ -572,10 +512,10 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
       // pre-activations arrive as the MUFU.EX2 argument (weights pre-multiplied by -log2 e): one rounding in front of the
       // exponential instead of two, like the MLP roles
       const float4 wv = LD4(&w.WE1s[k16 + k4]), bv = LD4(&w.bE1s[k16 + k4]);
-      e1[k4 + 0] = sigm_pre(fmaf(R, wv.x, bv.x));
-      e1[k4 + 1] = sigm_pre(fmaf(R, wv.y, bv.y));
-      e1[k4 + 2] = sigm_pre(fmaf(R, wv.z, bv.z));
-      e1[k4 + 3] = sigm_pre(fmaf(R, wv.w, bv.w));
+      // two units per instruction (FFMA2 / FADD2), the same operations and roundings as the scalar form
+      const float2 sa = sigm2_pre(f2fma(f2bc(R), make_float2(wv.x, wv.y), make_float2(bv.x, bv.y)));
+      const float2 sb = sigm2_pre(f2fma(f2bc(R), make_float2(wv.z, wv.w), make_float2(bv.z, bv.w)));
+      e1[k4 + 0] = sa.x; e1[k4 + 1] = sa.y; e1[k4 + 2] = sb.x; e1[k4 + 3] = sb.y;
       if (STASH) ST4(&E1row[(k16 + k4) ^ sx], e1[k4], e1[k4 + 1], e1[k4 + 2], e1[k4 + 3]);
     }
     tc_st_split16<true>(t0 + E_A_HI + k16, t0 + E_A_LO + k16, e1);
@@ -608,9 +548,11 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
       const float b2a[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
       float e2[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        e2[i] = sigm_pre(fmaf(v[j4 + i], NEG_LOG2E, b2a[i]));
+      for (int i = 0; i < 4; i += 2) {
+        const float2 s2 = sigm2_pre(f2fma(make_float2(v[j4 + i], v[j4 + i + 1]), f2bc(NEG_LOG2E), make_float2(b2a[i], b2a[i + 1])));
+        e2[i] = s2.x; e2[i + 1] = s2.y;
         E = fmaf(wEa[i], e2[i], E);
+        E = fmaf(wEa[i + 1], e2[i + 1], E);
       }
       if (STASH) ST4(&Vrow[(j16 + j4) ^ sx], e2[0], e2[1], e2[2], e2[3]);
     }
@@ -621,7 +563,11 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
 __device__ __forceinline__ float tc_gate_forward(const Wts& w, float R) {
   float g = w.bg;
 #pragma unroll
-  for (int i = 0; i < NL; i++) g = fmaf(w.wg[i], sigm_pre(fmaf(R, w.WgLs[i], w.bgLs[i])), g);
+  for (int i = 0; i < NL; i += 2) {
+    const float2 s2 = sigm2_pre(f2fma(f2bc(R), make_float2(w.WgLs[i], w.WgLs[i + 1]), make_float2(w.bgLs[i], w.bgLs[i + 1])));
+    g = fmaf(w.wg[i], s2.x, g);
+    g = fmaf(w.wg[i + 1], s2.y, g);
+  }
   return g;
 }
 
@@ -647,7 +593,11 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
       const float4 ev = LD4(&Vrow[(j16 + j4) ^ sx]), wEv = LD4(&w.wE[j16 + j4]);
       const float ea[4] = {ev.x, ev.y, ev.z, ev.w}, wEa[4] = {wEv.x, wEv.y, wEv.z, wEv.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) vbar[j4 + i] = Ebar * wEa[i] * fmaf(-ea[i], ea[i], ea[i]);
+      for (int i = 0; i < 4; i += 2) {
+        const float2 e = make_float2(ea[i], ea[i + 1]);
+        const float2 vb = f2mul(f2mul(f2bc(Ebar), make_float2(wEa[i], wEa[i + 1])), f2fma(f2neg(e), e, e));
+        vbar[j4 + i] = vb.x; vbar[j4 + i + 1] = vb.y;
+      }
       ST4(&Vrow[(j16 + j4) ^ sx], vbar[j4], vbar[j4 + 1], vbar[j4 + 2], vbar[j4 + 3]);
     }
     tc_st_split16<false>(t0 + E_A_HI + j16, t0 + E_A_LO + j16, vbar);
@@ -711,7 +661,11 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
       const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
       float ub[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) ub[i] = eb[k4 + i] * fmaf(-ea[i], ea[i], ea[i]);
+      for (int i = 0; i < 4; i += 2) {
+        const float2 e = make_float2(ea[i], ea[i + 1]);
+        const float2 u = f2mul(make_float2(eb[k4 + i], eb[k4 + i + 1]), f2fma(f2neg(e), e, e));
+        ub[i] = u.x; ub[i + 1] = u.y;
+      }
       ST4(&Vrow[(k16 + k4) ^ sx], ub[0], ub[1], ub[2], ub[3]);
     }
   }
@@ -719,12 +673,14 @@ __device__ __forceinline__ void tc_enet_backward(const Wts& w, TcCtx& c, float R
   {
     float ch[32];
 #pragma unroll
-    for (int i = 0; i < NL; i++) {
-      const float s = sigm_pre(fmaf(R, w.WgLs[i], w.bgLs[i]));
-      const float ub = gate_grads ? gbar * w.wg[i] * fmaf(-s, s, s) : 0.0f;
-      ch[i] = ub * R;
-      ch[10 + i] = ub;
-      ch[20 + i] = gate_grads ? gbar * s : 0.0f;
+    for (int i = 0; i < NL; i += 2) {
+      const float2 s2 = sigm2_pre(f2fma(f2bc(R), make_float2(w.WgLs[i], w.WgLs[i + 1]), make_float2(w.bgLs[i], w.bgLs[i + 1])));
+      const float2 ub = gate_grads ? f2mul(f2mul(f2bc(gbar), make_float2(w.wg[i], w.wg[i + 1])), f2fma(f2neg(s2), s2, s2)) : f2bc(0.0f);
+      const float2 ur = f2mul(ub, f2bc(R));
+      const float2 gs = gate_grads ? f2mul(f2bc(gbar), s2) : f2bc(0.0f);
+      ch[i] = ur.x; ch[i + 1] = ur.y;
+      ch[10 + i] = ub.x; ch[10 + i + 1] = ub.y;
+      ch[20 + i] = gs.x; ch[20 + i + 1] = gs.y;
     }
     ch[30] = gate_grads ? gbar : 0.0f;
     ch[31] = Ebar;
@@ -1174,10 +1130,11 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
       if (IS_MLP) {
   #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-          myrow[O_W2 + gq * NH + nt * 8 + 2 * tq] = acc.c[0][nt][0] + acc.c[1][nt][0];
-          myrow[O_W2 + gq * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][1] + acc.c[1][nt][1];
-          myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq] = acc.c[0][nt][2] + acc.c[1][nt][2];
-          myrow[O_W2 + (gq + 8) * NH + nt * 8 + 2 * tq + 1] = acc.c[0][nt][3] + acc.c[1][nt][3];
+          const int j0 = gq, j1 = gq + 8, k0 = nt * 8 + 2 * tq, k1 = k0 + 1;
+          myrow[O_W2 + j0 * NH + k0] = acc.c[0][nt][0] + acc.c[1][nt][0];
+          myrow[O_W2 + j0 * NH + k1] = acc.c[0][nt][1] + acc.c[1][nt][1];
+          myrow[O_W2 + j1 * NH + k0] = acc.c[0][nt][2] + acc.c[1][nt][2];
+          myrow[O_W2 + j1 * NH + k1] = acc.c[0][nt][3] + acc.c[1][nt][3];
         }
         // window index i (0..31) of each vector sum -> entry of the row
         auto e0 = [](int i) { return i < 16 ? O_B2 + i : O_WO + i - 16; };
@@ -1197,11 +1154,11 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         for (int mt = 0; mt < 2; mt++)
   #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
-            const int j = mt * 16 + gq, k = nt * 8 + 2 * tq;
-            myrow[O_WE2 + j * NE + k] = acc.c[mt][nt][0];
-            myrow[O_WE2 + j * NE + k + 1] = acc.c[mt][nt][1];
-            myrow[O_WE2 + (j + 8) * NE + k] = acc.c[mt][nt][2];
-            myrow[O_WE2 + (j + 8) * NE + k + 1] = acc.c[mt][nt][3];
+            const int j0 = mt * 16 + gq, j1 = j0 + 8, k0 = nt * 8 + 2 * tq, k1 = k0 + 1;
+            myrow[O_WE2 + j0 * NE + k0] = acc.c[mt][nt][0];
+            myrow[O_WE2 + j0 * NE + k1] = acc.c[mt][nt][1];
+            myrow[O_WE2 + j1 * NE + k0] = acc.c[mt][nt][2];
+            myrow[O_WE2 + j1 * NE + k1] = acc.c[mt][nt][3];
           }
         fold_pair(myrow, acc.s0, lane, [](int i) { return (int)O_WE + i; });
         fold_pair(myrow, acc.s1, lane, [](int i) { return (int)O_BE2 + i; });
