@@ -473,6 +473,9 @@ def main():
                     help="BASELINE config 4: points per step of the WHOLE job, sharded over the ranks (extra key config4_global_batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling-legs-only", action="store_true",
+                    help="N=1 run of a one-box scaling table: skip the legs that only run at N=1 (seam, reference autograd on the GPU, "
+                         "grid quadrature, cpu_baseline) so that the line has exactly the legs the N>1 lines have")
     ap.add_argument("--no-extras", action="store_true",
                     help="only the headline timed regions (profiling runs): no e2e / seam / config-4 / training-loop legs")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
@@ -718,7 +721,7 @@ def main():
             tr.close()
 
         # ---- N = 1: the seam itself, and two more reference points (BASELINE configs 2 and 5)
-        if world == 1:
+        if world == 1 and not args.scaling_legs_only:
             line_extra["seam_e2e"] = seam_e2e(pk, dev, n, max(20, min(K, 100)))
             if not args.no_cpu_baseline:
                 line_extra["reference_autograd_on_gpu"] = ref_autograd_on_gpu(load_theta(), dev)
@@ -771,7 +774,7 @@ def main():
             line["e2e"] = None
         if "dense_grid_inference" in line:
             line["dense_grid_inference"]["frac_of_fp32_peak"] = line["dense_grid_inference"]["tflops"] * 1e12 / fp32_peak
-        if not args.no_cpu_baseline and world == 1 and not args.no_extras:
+        if not args.no_cpu_baseline and world == 1 and not args.no_extras and not args.scaling_legs_only:
             v, cores, sample, _ = cpu_reference_points_per_s(np.ascontiguousarray(load_theta()), args.cpu_seconds, n)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample}
         emit(line)
