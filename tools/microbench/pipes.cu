@@ -179,6 +179,30 @@ __global__ void k_mma_tf32(float* out, const float* in) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the same with NC independent accumulator chains per warp: the dependent-accumulate latency of the legacy path
+// (1 warp per sub-core: cycles per HMMA = max(pipe time, latency / NC))
+template <int NC>
+__global__ void k_mma_tf32_chains(float* out, const float* in) {
+  float c[NC][4];
+  unsigned a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = __float_as_uint(in[i] + threadIdx.x);
+  b[0] = __float_as_uint(in[5]); b[1] = __float_as_uint(in[6]);
+#pragma unroll
+  for (int i = 0; i < NC; i++) for (int j = 0; j < 4; j++) c[i][j] = in[i + j];
+  for (int it = 0; it < ITERS / 4; it++) {
+#pragma unroll
+    for (int r = 0; r < 8 / NC; r++)
+#pragma unroll
+      for (int i = 0; i < NC; i++)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  float s = 0; for (int i = 0; i < NC; i++) for (int j = 0; j < 4; j++) s += c[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // legacy mma.sync m16n8k16 bf16 / f16 (fp32 accumulate), 8 independent accumulators: is the half-precision legacy path
 // faster per MAC than the TF32 one?  (It decides whether the cross terms of a 3xTF32 weight-gradient contraction are worth
 // moving to bf16.)
@@ -246,6 +270,13 @@ int main() {
   // 4 warps per SM (one per sub-core): what a single warp's 8 independent chains get
   run("mma_sync_tf32_m16n8k8_1warp_per_subcore", [&] { k_mma_tf32<<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
   run("mma_sync_bf16_m16n8k16_1warp_per_subcore", [&] { k_mma_h16<0><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 2048.0 / 32.0, 128, 148, "MAC/s");
+  // dependent-accumulate latency: 1 warp per sub-core, 1 / 2 / 4 / 8 chains; and 3 warps per sub-core with 2 and 4 chains each
+  run("mma_tf32_1warp_1chain", [&] { k_mma_tf32_chains<1><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
+  run("mma_tf32_1warp_2chains", [&] { k_mma_tf32_chains<2><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
+  run("mma_tf32_1warp_4chains", [&] { k_mma_tf32_chains<4><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
+  run("mma_tf32_1warp_8chains", [&] { k_mma_tf32_chains<8><<<148, 128>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 128, 148, "MAC/s");
+  run("mma_tf32_3warps_2chains", [&] { k_mma_tf32_chains<2><<<148, 384>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 384, 148, "MAC/s");
+  run("mma_tf32_3warps_4chains", [&] { k_mma_tf32_chains<4><<<148, 384>>>(out, in); }, ITERS / 4 * 8.0 * 1024.0 / 32.0, 384, 148, "MAC/s");
   // long FP32 run to read the sustained clock with nvidia-smi
   for (int i = 0; i < 400; i++) k_ffma2<16><<<B, T>>>(out, in);
   CK(cudaDeviceSynchronize());
