@@ -149,7 +149,12 @@ __device__ __forceinline__ RawPt coord_stage_read(const StepParams& p, const uns
 __device__ __forceinline__ void tc_role_sync(const TcCtx& c) {
   tc_wait_st();
   tc_fence_before();
-  named_barrier(c.bar_id, 128);
+  // Only the issuing warp has to know that all four warps' operand rows are in tensor memory: it syncs, the other three
+  // signal and go on (their next use of the result waits on the MMA's mbarrier anyway; their stash rows are their own).
+  // v15: step -1.1 %, same bits (profiles/r02_ar_ab_role_barrier_arrive.log).  Choosing the issuer dynamically - the first
+  // warp to arrive, or the last one with no barrier at all - measured 1.6 % / 2.7 % SLOWER than the fixed one (r02_as_*).
+  if (c.issuer) named_barrier(c.bar_id, 128);
+  else asm volatile("bar.arrive %0, %1;" ::"r"(c.bar_id), "r"(128) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -791,7 +796,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
   const bool cbulk = INLINE && TRAIN && COORD_AHEAD == 1 && !p.grid.on &&
                      ((((uintptr_t)p.x | (uintptr_t)p.y | (uintptr_t)p.z | (uintptr_t)p.R | (uintptr_t)p.mask) & 15u) == 0);
   auto tile_bulk = [&](long long st) { return INLINE && cbulk && (st * 128 + 128 <= p.n); };
-  const bool bulk_issuer = stager && grp == 3 && lane == 0;
+  const bool bulk_issuer = stager && grp == 0 && lane == 0;  // in the warp that SYNCS on the E-net role barrier (see below)
   if (stager && tile_bulk(blockIdx.x)) {
     if (bulk_issuer) coord_stage_issue_bulk(p, cstage, &cfull[0], blockIdx.x);
   } else if (stager) {
@@ -954,8 +959,9 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
           unsigned char* nbuf = cstage + ((it + COORD_AHEAD) % COORD_STAGES) * COORD_STAGE_BYTES;
           if (tile_bulk(stn)) {
             // (training launches only.)  The target buffer was read at the top of the previous super-tile; this thread
-            // has since passed the E-net role barrier of that tile's reverse sweep, which every E-net warp reaches after
-            // its group's mid-tile barrier, i.e. after all 12 warps had read their coordinates.
+            // sits in the E-net role's issuing warp and has since SYNCED on the role barriers of that tile (the other
+            // three warps only signal there), i.e. all four E-net warps - the only readers of the stage in training
+            // launches - had read their coordinates.
             if (bulk_issuer) coord_stage_issue_bulk(p, nbuf, &cfull[(it + COORD_AHEAD) % COORD_STAGES], stn);
           } else {
             coord_stage_issue(p, nbuf, slot, in < p.n ? in : p.n - 1);
