@@ -505,9 +505,10 @@ __device__ __forceinline__ void tc_mlp_extras_only(float* __restrict__ Hs, int l
 // ---------------------------------------------------------------------------------------------
 // E(R) network (poc/main.py:249-253; train.py:50-52) and gate (poc/main.py:262-264; train.py:48-49)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tc_gate_forward(const Wts& w, float R);
 template <bool STASH>
 __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R, float* __restrict__ E1row,
-                                                 float* __restrict__ Vrow, int sx) {
+                                                 float* __restrict__ Vrow, int sx, float& gate_out) {
   const uint32_t t0 = c.tlane + TC_E_BASE;
 #pragma unroll
   for (int k16 = 0; k16 < NE; k16 += 16) {
@@ -539,6 +540,10 @@ __device__ __forceinline__ float tc_enet_forward(const Wts& w, TcCtx& c, float R
     tc_commit(c.mbar);
   }
   __syncwarp();
+  // the gate (ten sigmoids of R, independent of the MMA) while the tensor core runs: this role has no stash writes to hide
+  // its forward MMAs behind (-0.2 %, same bits, profiles/r02_ay_*; moving the e1 stash writes here as well keeps 32 more
+  // values live across the barrier and is 1.6 % slower, r02_ax_*)
+  gate_out = tc_gate_forward(w, R);
   tc_wait_mma(c);
   TL(3);
   float E = w.bE;
@@ -983,8 +988,8 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         tc_mlp_forward<TRAIN>(w, c, cb, a, b, al1, al2, al11, al12, al22, Hs + lane * ROWH, Gs + lane * ROWH, sx, Nv, Dv);
         box[role * 32 + lane] = make_float2(Nv, Dv);
       } else {
-        const float E = tc_enet_forward<TRAIN>(w, c, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx);
-        const float gt = tc_gate_forward(w, g.R);
+        float gt;
+        const float E = tc_enet_forward<TRAIN>(w, c, g.R, Hs + lane * ROWE, Gs + lane * ROWE, sx, gt);
         box[2 * 32 + lane] = make_float2(E, gt);
       }
       TL(5);
