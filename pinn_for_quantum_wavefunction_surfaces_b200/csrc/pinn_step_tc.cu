@@ -911,7 +911,25 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
     }
     __syncthreads();
     TLK(1);
-    for (long long st = blockIdx.x; st < nsuper; st += gridDim.x, ++it) {
+    // Dense-grid quadrature: R is one number for the whole launch, so E(R) and the gate are too.  The E-net role evaluates
+    // them ONCE (through the same tensor-core path, i.e. the same bits every point used to get), leaves them in both mailbox
+    // buffers of its group and sits the tile loop out: the two MLP warps of a scheduler have it to themselves (10^8-point
+    // quadrature 8.3e9 -> 1.03e10 points/s, same bits).  Letting the idle E-net warps also produce the geometry one tile ahead
+    // (filled / consumed barriers, two buffers) is correct and SLOWER, 9.3e9: one producer warp per group with 64-bit index
+    // divisions does not keep up with two MLP warps whose inference tile is short.
+    const bool enet_once = !TRAIN && p.grid.on;
+    if (enet_once) {
+      if (!IS_MLP) {
+        const float Rg = (float)p.grid.R;
+        float gt;
+        const float E = tc_enet_forward<false>(w, c, Rg, Hs + lane * ROWE, Gs + lane * ROWE, sx, gt);
+        gbox[2 * 32 + lane] = make_float2(E, gt);
+        gbox[3 * 32 + 2 * 32 + lane] = make_float2(E, gt);
+        if (blockIdx.x == 0 && grp == 0 && lane == 0) p.grid.partials[8 * (size_t)gridDim.x] = (double)E;  // E(R) of the launch
+      }
+      named_barrier(1 + grp, (NEV + 1) * 32);
+    }
+    for (long long st = blockIdx.x; st < nsuper && !(enet_once && !IS_MLP); st += gridDim.x, ++it) {
       const long long pidx = st * 128 + slot;
       const bool valid = pidx < p.n;
       const long long pi = valid ? pidx : (p.n - 1);
@@ -1001,7 +1019,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         if (stn < nsuper && tile_bulk(stn))
           mbar_wait(smem_u32(&cfull[(it + 1) % COORD_STAGES]), (uint32_t)((it + 1) / COORD_STAGES) & 1u);
       }
-      named_barrier(1 + grp, (NEV + 1) * 32);
+      named_barrier(1 + grp, enet_once ? NEV * 32 : (NEV + 1) * 32);
       TL(6);
 
       // ---- combine (every role recomputes the few scalars it needs) ----
@@ -1034,9 +1052,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
             gs2 += wq * (double)(fs * hl);
             gs3 += wq * (double)(fs * fs);
             gs4 += wq * (double)(vr * psi * psi);
-          } else if (!IS_MLP && st == 0 && grp == 0 && lane == 0) {
-            p.grid.partials[8 * (size_t)gridDim.x] = (double)E;  // E(R) of the launch, behind the partial rows
-          }
+          }  // (E(R) of the launch was stored behind the partial rows by the E-net role, in front of the loop)
           continue;
         }
         if (valid) {
