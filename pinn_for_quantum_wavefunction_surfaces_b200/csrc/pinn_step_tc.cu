@@ -1040,7 +1040,7 @@ pinn_step_tc_kernel(const __grid_constant__ typename std::conditional<INLINE, Tc
         if (p.grid.on) {
           if (valid && role == 0) {
             int ix, iy, iz;
-            grid_ijk(p.grid, pidx, ix, iy, iz);
+            grid_ijk(p.grid, pi, ix, iy, iz);  // (pi == pidx for a valid point: the same expression as in tc_grid_point above)
             const double wq = p.grid.wx[ix] * p.grid.wy[iy] * p.grid.wz[iz];
             // Hartree form of H psi (poc/main.py:118-120) with the cusp terms cancelled analytically, and its LCAO part
             const float hl = fmaf(-0.5f, fs, -fmaf(g.f1, g.ir2, g.f2 * g.ir1));

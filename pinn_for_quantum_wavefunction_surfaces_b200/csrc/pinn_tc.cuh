@@ -173,6 +173,15 @@ __device__ __forceinline__ void tc_wait_mma(TcCtx& c) {
 // coordinates of point `i`: from the caller's arrays, or generated from the grid descriptor (meshgrid 'ij' order;
 // positions are formed in double like the reference's linspace and rounded once, the nucleus offsets before rounding)
 __device__ __forceinline__ void grid_ijk(const GridDesc& g, long long i, int& ix, int& iy, int& iz) {
+  if ((unsigned long long)i < 0x80000000ull) {  // every practical grid (464^3 = 1.0e8): 32-bit divisions, a fifth of the code
+    const unsigned u = (unsigned)i, nz = (unsigned)g.nz, ny = (unsigned)g.ny;
+    const unsigned r = u / nz;
+    iz = (int)(u - r * nz);
+    const unsigned q = r / ny;
+    iy = (int)(r - q * ny);
+    ix = (int)q;
+    return;
+  }
   iz = (int)(i % g.nz);
   const long long r = i / g.nz;
   iy = (int)(r % g.ny);
