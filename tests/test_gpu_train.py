@@ -419,6 +419,27 @@ def test_grid_energies_vs_oracle(n, rule, ck):
         assert abs(pk.analysis.dEdR_int(th32, Ri, prm, rule=rule) - (ref["dVdR_psi2"] / ref["psi2"] - 0.5 / Ri ** 2)) < 1e-4
 
 
+@pytest.mark.parametrize("variant", ["poc", "trainpy"])
+def test_grid_sums_equal_the_per_point_fields_summed_on_the_host(variant, ck, init_theta):
+    """Grid launches evaluate E(R) and the gate once per CTA and keep the E-net role out of the tile loop; per-point
+    inference (`fields`) evaluates them at every point.  Same psi, H psi and E: the quadrature of the per-point fields with
+    the same weights is the grid kernel's sums (many super-tiles per CTA, both forms of the model, ragged last tile)."""
+    th32 = (ck["ionHsym_fineTune"] if variant == "poc" else init_theta).astype(np.float32)
+    n, Ri = 59, 1.3                                        # 205 379 points = 1605 super-tiles, the last one ragged
+    ax = np.linspace(-18, 18, n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel())).to(dev())
+    f = pk.fields(variant, t(X), t(Y), t(Z), t(np.full(X.size, Ri)), torch.from_numpy(th32).to(dev()))
+    psi, hpsi = f["psi"].cpu().numpy(), f["hpsi"].cpu().numpy()
+    w1 = sp.weights_avg(n, ax[1] - ax[0])
+    W = np.einsum("i,j,k->ijk", w1, w1, w1).ravel()
+    got = pk.analysis.grid_sums(th32, Ri, {"n_test": n}, variant=variant)
+    ref = {"psiHpsi": W @ (psi * hpsi).astype(np.float64), "psi2": W @ (psi * psi).astype(np.float64)}
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-9 * abs(ref[k]), (k, got[k], ref[k])
+    assert got["E_net"] == float(f["E"].cpu().numpy()[-1])
+
+
 def test_grid_point_on_a_nucleus_gives_nan_like_the_reference(ck):
     """Odd n_test puts x = y = z = 0 ... on the grid; with R a multiple of the spacing a grid point sits ON a nucleus, where the
     reference divides by r = 0 without a guard (poc/main.py:111-120, 442-454): its E_integral is NaN, its E_net is fine
