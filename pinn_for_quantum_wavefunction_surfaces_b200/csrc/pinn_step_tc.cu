@@ -338,6 +338,7 @@ __device__ __forceinline__ void tc_mlp_backward(const Wts& w, TcCtx& c, uint32_t
     // Eight units at a time: all six loads of a block precede its stores (vbar lo of channels 2, 3 lands on the block's
     // own t / A columns), and a block's vbar goes to tensor memory and to the stash at once - nothing stays in registers.
     const uint32_t t0 = c.tlane + cb;
+    tc_wait_st();  // the forward's parking stores (long complete by now; the wait makes the order explicit)
 #pragma unroll
     for (int j8 = 0; j8 < NH; j8 += 8) {
       float T[8], A[8], B1[8], B2[8], C[8], GD[8];
